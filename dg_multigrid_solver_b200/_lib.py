@@ -1,0 +1,148 @@
+"""ctypes binding of libdgb200.so (include/dgb200.h).  PyTorch only owns the device buffers;
+every call passes raw device pointers (tensor.data_ptr()) and the current CUDA stream.
+
+There is NO CPU fallback: if the CUDA extension is missing or no GPU is visible, the
+product path raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdgb200.so")
+_lib = None
+
+c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+
+
+class DgbError(RuntimeError):
+    pass
+
+
+class SmootherCtl(ctypes.Structure):
+    """dgb_smoother_ctl (include/dgb200.h)."""
+    _fields_ = [("res0", c_f64), ("ratio", c_f64), ("skip", c_i32), ("diverged", c_i32),
+                ("iters", c_i32), ("calls", c_i32)]
+
+
+class Level(ctypes.Structure):
+    """dgb_level (include/dgb200.h)."""
+    _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
+                ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp),
+                ("rhs", c_vp), ("u", c_vp), ("r", c_vp),
+                ("transfer_kind", c_i32), ("nc", c_i32), ("nf", c_i32),
+                ("R", c_vp), ("P", c_vp),
+                ("smoother", c_i32), ("direction", c_i32),
+                ("pre_iterations", c_i32), ("post_iterations", c_i32), ("omega", c_f64)]
+
+
+class VcycleOpts(ctypes.Structure):
+    _fields_ = [("gs_mode", c_i32), ("check_residual", c_i32), ("coarse_iterations", c_i32),
+                ("reserved", c_i32)]
+
+
+class TablesDesc(ctypes.Structure):
+    _fields_ = [("Pg", c_i32), ("p", c_i32), ("nq1", c_i32), ("cf", c_i32)] + \
+        [(n, c_vp) for n in ("h_V", "h_Vr", "h_Vs", "h_w2", "h_w1", "h_Vf", "h_Vrf", "h_Vsf",
+                             "h_GX", "h_GR", "h_GS", "h_FX", "h_FR", "h_FS", "h_sub_vol", "h_sub_face")]
+
+
+GS_LEXICOGRAPHIC, GS_REDBLACK = 0, 1
+TRANSFER_P, TRANSFER_H = 1, 2
+SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_seidel": 2}
+FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV = 1, 2, 4
+
+# name -> (restype, argtypes); every symbol include/dgb200.h declares
+SIGNATURES = {
+    "dgb_abi_version": (c_i32, []),
+    "dgb_last_error": (ctypes.c_char_p, []),
+    "dgb_sm_count": (c_i32, []),
+    "dgb_partials_len": (c_i32, []),
+    "dgb_launch_count": (ctypes.c_longlong, [c_i32]),
+    "dgb_bsr_apply": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_bsr_residual": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_bsr_residual_skip": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dgb_block_diag_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_gs_pass": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_relax_sweep": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "dgb_smoother_check": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "dgb_block_gauss_seidel_pyamg": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp,
+                                             c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_restrict": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_prolong_add": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_vcycle": (c_i32, [ctypes.POINTER(Level), c_i32, ctypes.POINTER(VcycleOpts), c_vp, c_vp, c_vp, c_vp]),
+    "dgb_tables_create": (c_i32, [ctypes.POINTER(TablesDesc), ctypes.POINTER(c_vp)]),
+    "dgb_tables_destroy": (None, [c_vp]),
+    "dgb_metrics": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_poisson_nnzb": (c_i64, [c_i32, c_i32, c_i32]),
+    "dgb_assemble_poisson": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_i32,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_assemble_rhs": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64,
+                                 c_i32, c_vp, c_vp]),
+}
+
+
+def load(path=None):
+    """dlopen libdgb200.so and bind every declared symbol.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise DgbError(f"{path} not found: build it with `python -m dg_multigrid_solver_b200.build` "
+                       "(there is no CPU fallback)")
+    L = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.dgb_abi_version() != 1:
+        raise DgbError("libdgb200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().dgb_last_error().decode(errors="replace")
+        raise DgbError(f"{what} failed (rc={rc}): {msg}")
+
+
+def call(name, *args):
+    L = load()
+    conv = []
+    for a in args:
+        if hasattr(a, "data_ptr") or isinstance(a, np.ndarray):
+            conv.append(ptr(a))
+        else:
+            conv.append(a)
+    rc = getattr(L, name)(*conv)
+    check(rc, name)
+    return rc
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise DgbError("no CUDA device visible: dg_multigrid_solver_b200 has no CPU path")
+    load()
+    return torch

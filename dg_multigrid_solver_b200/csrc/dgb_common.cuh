@@ -1,0 +1,86 @@
+// dgb_common.cuh -- shared helpers for libdgb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dgb200.h"
+
+namespace dgb {
+
+// Grid cap for kernels that emit one partial sum per CTA (fixed-order second stage).
+constexpr int kMaxPartials = 4096;
+
+void set_error(const char *fmt, ...);
+int sm_count();
+extern long long g_launches;   // kernels launched by this library (dgb_launch_count)
+
+#define DGB_CUDA_OK(expr)                                                               \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            dgb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,                 \
+                           cudaGetErrorString(_e));                                     \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define DGB_LAUNCH_OK()                                                                 \
+    do {                                                                                \
+        ++dgb::g_launches;                                                              \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) {                                                        \
+            dgb::set_error("%s:%d launch -> %s", __FILE__, __LINE__,                    \
+                           cudaGetErrorString(_e));                                     \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define DGB_ARG(cond)                                                                   \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            dgb::set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond);        \
+            return 1;                                                                   \
+        }                                                                               \
+    } while (0)
+
+// Block sizes with a compiled specialisation: (p+1)^2 for p = 0..5, plus the Stokes
+// local-order block 2*9+4 = 22 (p_u=2, p_p=1).
+#define DGB_DISPATCH_B(b, ...)                                                          \
+    switch (b) {                                                                        \
+    case 1: { constexpr int B = 1; __VA_ARGS__; } break;                                \
+    case 4: { constexpr int B = 4; __VA_ARGS__; } break;                                \
+    case 9: { constexpr int B = 9; __VA_ARGS__; } break;                                \
+    case 16: { constexpr int B = 16; __VA_ARGS__; } break;                              \
+    case 22: { constexpr int B = 22; __VA_ARGS__; } break;                              \
+    case 25: { constexpr int B = 25; __VA_ARGS__; } break;                              \
+    case 36: { constexpr int B = 36; __VA_ARGS__; } break;                              \
+    default:                                                                            \
+        dgb::set_error("unsupported block size b=%d", (int)(b));                        \
+        return 2;                                                                       \
+    }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CTA-wide sum (fixed shape => deterministic); result valid in thread 0.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *s_red /* [32] */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (lane < (NT + 31) / 32) ? s_red[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    __syncthreads();
+    return t;
+}
+
+}  // namespace dgb

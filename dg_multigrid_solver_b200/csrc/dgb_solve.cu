@@ -1,0 +1,561 @@
+// dgb_solve.cu -- solve-phase kernels (apply / residual / smoothers / transfers), generic
+// row-per-thread versions.  These are the always-available path for any BSR structure; the
+// TMA-pipelined streaming kernels in dgb_stream.cu take over for the hot configurations.
+//
+// Reference semantics restated here:
+//   y = A x            scipy bsr_matvec               <- dgfem/solver.py:117,119,150
+//   block GS pass      pyamg amg_core.block_gauss_seidel <- dgfem/pyamg_relaxation.py:252-255
+//   block Jacobi / GS  dgfem/relaxation.py:123-195
+//   transfers          dgfem/solver.py:152-193
+#include <stdarg.h>
+
+#include "dgb_common.cuh"
+
+namespace dgb {
+
+static thread_local char g_err[512] = "";
+long long g_launches = 0;
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// element selection for the relaxation kernels
+struct Sel {
+    int mode;   // 0: all elements; 1: colour class (i+j)&1 == sel; 2: anti-diagonal i+j == sel
+    int sel;
+    int Ni, Nj;
+    int i_lo;   // mode 2: first i on the diagonal
+    int count;  // number of candidate items (mode 0/1: Ni*Nj, mode 2: elements on the diagonal)
+};
+
+__device__ __forceinline__ int sel_element(const Sel &s, int idx) {
+    if (s.mode == 0) return idx;
+    if (s.mode == 1) {
+        const int i = idx % s.Ni, j = idx / s.Ni;
+        return (((i + j) & 1) == s.sel) ? idx : -1;
+    }
+    const int i = s.i_lo + idx;
+    return (s.sel - i) * s.Ni + i;
+}
+
+enum { MODE_APPLY = 0, MODE_RESIDUAL = 1, MODE_RELAX = 2 };
+
+template <int B>
+struct RowCfg {
+    static constexpr int EPB = (256 / B) > 0 ? (256 / B) : 1;  // elements per CTA
+    static constexpr int NT = ((EPB * B + 31) / 32) * 32;      // threads per CTA
+};
+
+// One thread per scalar row (element e, row r).  Blocks are read straight from global
+// memory (row-major 8*B-byte rows per thread; the L1 serves the neighbouring columns).
+template <int B, int MODE>
+__global__ void __launch_bounds__(RowCfg<B>::NT)
+k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
+       const int32_t *__restrict__ indptr, const double *__restrict__ dinv,
+       const double *__restrict__ rhs, const double *x_in, double *x_out, double *partials,
+       double omega, Sel sel, const int32_t *__restrict__ skip) {
+    constexpr int EPB = RowCfg<B>::EPB;
+    constexpr int NT = RowCfg<B>::NT;
+    if (skip != nullptr && *skip != 0) return;
+    __shared__ double s_rsum[MODE == MODE_RELAX ? EPB * B : 1];
+    __shared__ double s_red[32];
+    const int el = threadIdx.x / B;
+    const int r = threadIdx.x - el * B;
+    const bool lane_ok = el < EPB;
+    const int ntiles = (sel.count + EPB - 1) / EPB;
+    double sumsq = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int idx = tile * EPB + el;
+        int e = -1;
+        if (lane_ok && idx < sel.count) e = sel_element(sel, idx);
+        double acc = 0.0;
+        if (e >= 0) {
+            const int j0 = indptr[e], j1 = indptr[e + 1];
+            for (int jj = j0; jj < j1; ++jj) {
+                const int col = indices[jj];
+                if (MODE == MODE_RELAX && col == e) continue;
+                const double *a = data + ((size_t)jj * B + r) * B;
+                const double *xv = x_in + (size_t)col * B;
+                double t = 0.0;
+#pragma unroll
+                for (int c = 0; c < B; ++c) t = fma(a[c], xv[c], t);
+                acc += t;
+            }
+        }
+        if (MODE == MODE_APPLY) {
+            if (e >= 0) x_out[(size_t)e * B + r] = acc;
+        } else if (MODE == MODE_RESIDUAL) {
+            if (e >= 0) {
+                const double res = rhs[(size_t)e * B + r] - acc;
+                if (x_out != nullptr) x_out[(size_t)e * B + r] = res;
+                sumsq = fma(res, res, sumsq);
+            }
+        } else {
+            if (e >= 0) s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
+            __syncthreads();
+            if (e >= 0) {
+                const double *d = dinv + ((size_t)e * B + r) * B;
+                double t = 0.0;
+#pragma unroll
+                for (int c = 0; c < B; ++c) t = fma(d[c], s_rsum[el * B + c], t);
+                const double xo = x_in[(size_t)e * B + r];
+                x_out[(size_t)e * B + r] = (omega == 1.0) ? t : omega * t + (1.0 - omega) * xo;
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == MODE_RESIDUAL) {
+        const double t = block_sum<NT>(sumsq, s_red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = t;
+    }
+}
+
+// fixed-order sum of the per-CTA partials -> *out
+__global__ void __launch_bounds__(1024)
+k_sum_partials(const double *__restrict__ partials, int n, double *out,
+               const int32_t *__restrict__ skip) {
+    if (skip != nullptr && *skip != 0) return;
+    __shared__ double s_red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) v += partials[i];
+    const double t = block_sum<1024>(v, s_red);
+    if (threadIdx.x == 0) *out = t;
+}
+
+__global__ void __launch_bounds__(256)
+k_sumsq(const double *__restrict__ v, int64_t n, double *partials) {
+    __shared__ double s_red[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+        s = fma(v[i], v[i], s);
+    const double t = block_sum<256>(s, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+static int rows_grid(int count, int epb) {
+    const int ntiles = (count + epb - 1) / epb;
+    int g = sm_count() * 8;
+    if (g > kMaxPartials) g = kMaxPartials;
+    if (g > ntiles) g = ntiles;
+    return g < 1 ? 1 : g;
+}
+
+// ---------------------------------------------------------------------------------------
+// smoother control (device-side early exit; relaxation.py:202-216)
+__global__ void k_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, double n) {
+    ctl->res0 = sqrt(*sumsq / n);
+    ctl->ratio = 1.0;
+    ctl->skip = 0;
+    ctl->diverged = 0;
+    ctl->iters = 0;
+    ctl->calls += 1;
+}
+__global__ void k_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, double n) {
+    if (ctl->skip) return;
+    const double ratio = sqrt(*sumsq / n) / ctl->res0;
+    ctl->ratio = ratio;
+    ctl->iters += 1;
+    if (ratio < 1e-6) {
+        ctl->skip = 1;
+    } else if (ratio > 1e10) {
+        ctl->diverged = 1;
+        ctl->skip = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: in-place Gauss-Jordan inverse with partial pivoting, one warp per block, matrix in smem
+template <int B>
+__global__ void __launch_bounds__(128)
+k_block_diag_inverse(const double *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int32_t *__restrict__ indptr, int n_brow, double *dinv, int32_t *info) {
+    constexpr int WPB = 4;
+    __shared__ double s_a[WPB][B * B];
+    __shared__ int s_piv[WPB][B];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * WPB + w;
+    if (e >= n_brow) return;
+    double *a = s_a[w];
+    // gather (sum of) the diagonal block(s) of row e
+    for (int t = lane; t < B * B; t += 32) a[t] = 0.0;
+    __syncwarp();
+    for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+        if (indices[jj] != e) continue;
+        for (int t = lane; t < B * B; t += 32) a[t] += data[(size_t)jj * B * B + t];
+        __syncwarp();
+    }
+    for (int k = 0; k < B; ++k) {
+        // pivot search over rows k..B-1 (first maximum wins => deterministic)
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + lane; i < B; i += 32) {
+            const double v = fabs(a[i * B + k]);
+            if (v > best) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) s_piv[w][k] = bi;
+        if (best == 0.0 || !(best == best)) {
+            if (lane == 0) atomicCAS(info, 0, e + 1);
+            // leave a zero block behind (the reference's pinv would return the pseudo-inverse)
+            for (int t = lane; t < B * B; t += 32) dinv[(size_t)e * B * B + t] = 0.0;
+            return;
+        }
+        if (bi != k) {
+            for (int c = lane; c < B; c += 32) {
+                const double t = a[k * B + c];
+                a[k * B + c] = a[bi * B + c];
+                a[bi * B + c] = t;
+            }
+        }
+        __syncwarp();
+        const double pinv = 1.0 / a[k * B + k];
+        __syncwarp();
+        for (int c = lane; c < B; c += 32) a[k * B + c] = (c == k) ? pinv : a[k * B + c] * pinv;
+        __syncwarp();
+        // eliminate column k from all other rows: items (i, c)
+        for (int t = lane; t < B * B; t += 32) {
+            const int i = t / B, c = t - i * B;
+            if (i == k) continue;
+            const double f = a[i * B + k];
+            // column k itself must be handled last for each row; use the saved factor
+            if (c != k) a[t] = fma(-f, a[k * B + c], a[t]);
+        }
+        __syncwarp();
+        for (int i = lane; i < B; i += 32)
+            if (i != k) a[i * B + k] = -a[i * B + k] * pinv;
+        __syncwarp();
+    }
+    // undo the row interchanges as column interchanges, in reverse order
+    for (int k = B - 1; k >= 0; --k) {
+        const int p = s_piv[w][k];
+        if (p != k) {
+            for (int i = lane; i < B; i += 32) {
+                const double t = a[i * B + k];
+                a[i * B + k] = a[i * B + p];
+                a[i * B + p] = t;
+            }
+        }
+        __syncwarp();
+    }
+    for (int t = lane; t < B * B; t += 32) dinv[(size_t)e * B * B + t] = a[t];
+}
+
+template <int B>
+__global__ void __launch_bounds__(256)
+k_build_gs_stream(const double *__restrict__ data, const int32_t *__restrict__ indices,
+                  const int32_t *__restrict__ indptr, const double *__restrict__ dinv, int n_brow,
+                  double *gs) {
+    // one warp per block row
+    const int e = (int)(((size_t)blockIdx.x * 256 + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_brow) return;
+    for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+        const double *src = (indices[jj] == e) ? dinv + (size_t)e * B * B : data + (size_t)jj * B * B;
+        for (int t = lane; t < B * B; t += 32) gs[(size_t)jj * B * B + t] = src[t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K9: transfers.  One thread per output scalar; R/P (<= 16x36 doubles) staged in smem.
+// H gather (solver.py:164): flat fine element = A0*(4*Nj_c) + a1*(2*Nj_c) + 2*A2 + a3 with
+// coarse row K = A0*Nj_c + A2 and child slot a1*2 + a3 -- the reference's literal
+// reshape((Ni_c,2,Nj_c,2,b)).transpose(0,2,1,3,4), valid as geometry for square grids only.
+__device__ __forceinline__ size_t h_fine_elem(int K, int child, int Nj_c) {
+    const int A0 = K / Nj_c, A2 = K - A0 * Nj_c;
+    const int a1 = child >> 1, a3 = child & 1;
+    return (size_t)A0 * (4 * (size_t)Nj_c) + (size_t)a1 * (2 * (size_t)Nj_c) + 2 * (size_t)A2 + a3;
+}
+
+__global__ void __launch_bounds__(256)
+k_restrict(int kind, const double *__restrict__ R, int nc, int nf, int Nj_c, int64_t n_coarse_el,
+           const double *__restrict__ fine, double *__restrict__ coarse) {
+    extern __shared__ double s_R[];
+    for (int t = threadIdx.x; t < nc * nf; t += blockDim.x) s_R[t] = R[t];
+    __syncthreads();
+    const int64_t total = n_coarse_el * nc;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = o / nc;
+        const int a = (int)(o - K * nc);
+        double acc = 0.0;
+        if (kind == DGB_TRANSFER_P) {
+            const double *f = fine + K * nf;
+            for (int c = 0; c < nf; ++c) acc = fma(s_R[a * nf + c], f[c], acc);
+        } else {
+            const int bf = nf / 4;
+            for (int child = 0; child < 4; ++child) {
+                const double *f = fine + h_fine_elem((int)K, child, Nj_c) * bf;
+                for (int d = 0; d < bf; ++d) acc = fma(s_R[a * nf + child * bf + d], f[d], acc);
+            }
+        }
+        coarse[o] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_prolong_add(int kind, const double *__restrict__ P, int nc, int nf, int Nj_c, int64_t n_coarse_el,
+              const double *__restrict__ coarse, double *__restrict__ fine) {
+    extern __shared__ double s_P[];
+    for (int t = threadIdx.x; t < nc * nf; t += blockDim.x) s_P[t] = P[t];
+    __syncthreads();
+    const int64_t total = n_coarse_el * nf;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = o / nf;
+        const int f = (int)(o - K * nf);
+        const double *uc = coarse + K * nc;
+        double acc = 0.0;
+        for (int a = 0; a < nc; ++a) acc = fma(s_P[f * nc + a], uc[a], acc);
+        if (kind == DGB_TRANSFER_P) {
+            fine[o] += acc;
+        } else {
+            const int bf = nf / 4;
+            const int child = f / bf, d = f - child * bf;
+            fine[h_fine_elem((int)K, child, Nj_c) * bf + d] += acc;
+        }
+    }
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int dgb_abi_version(void) { return DGB_ABI_VERSION; }
+const char *dgb_last_error(void) { return g_err; }
+int dgb_sm_count(void) { return sm_count(); }
+int dgb_partials_len(void) { return kMaxPartials; }
+long long dgb_launch_count(int32_t reset) {
+    const long long n = g_launches;
+    if (reset) g_launches = 0;
+    return n;
+}
+
+int dgb_bsr_apply(const double *data, const int32_t *indices, const int32_t *indptr,
+                  int32_t n_brow, int32_t b, const double *x, double *y, void *stream) {
+    DGB_ARG(data && indices && indptr && x && y && n_brow >= 0);
+    if (n_brow == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    Sel sel{0, 0, n_brow, 1, 0, n_brow};
+    DGB_DISPATCH_B(b, k_rows<B, MODE_APPLY><<<rows_grid(n_brow, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+                          data, indices, indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_bsr_residual_skip(const double *data, const int32_t *indices, const int32_t *indptr,
+                          int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
+                          double *partials, double *sumsq, const int32_t *skip, void *stream) {
+    DGB_ARG(data && indices && indptr && x && rhs && partials && sumsq && n_brow > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    Sel sel{0, 0, n_brow, 1, 0, n_brow};
+    int grid = 1;
+    DGB_DISPATCH_B(b, grid = rows_grid(n_brow, RowCfg<B>::EPB);
+                   k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
+                       data, indices, indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
+    DGB_LAUNCH_OK();
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_bsr_residual(const double *data, const int32_t *indices, const int32_t *indptr,
+                     int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
+                     double *partials, double *sumsq, void *stream) {
+    return dgb_bsr_residual_skip(data, indices, indptr, n_brow, b, rhs, x, r, partials, sumsq,
+                                 nullptr, stream);
+}
+
+int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream) {
+    DGB_ARG(v && partials && sumsq && n > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    k_sumsq<<<grid, 256, 0, st>>>(v, n, partials);
+    DGB_LAUNCH_OK();
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, nullptr);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_block_diag_inverse(const double *data, const int32_t *indices, const int32_t *indptr,
+                           int32_t n_brow, int32_t b, double *dinv, int32_t *info, void *stream) {
+    DGB_ARG(data && indices && indptr && dinv && info && n_brow > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    DGB_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+    DGB_DISPATCH_B(b, k_block_diag_inverse<B><<<(n_brow + 3) / 4, 128, 0, st>>>(data, indices, indptr,
+                                                                              n_brow, dinv, info));
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_t *indptr,
+                        const double *dinv, int32_t n_brow, int32_t b, double *gs_data,
+                        void *stream) {
+    DGB_ARG(data && indices && indptr && dinv && gs_data && n_brow > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)(((size_t)n_brow * 32 + 255) / 256);
+    DGB_DISPATCH_B(b, k_build_gs_stream<B><<<grid, 256, 0, st>>>(data, indices, indptr, dinv, n_brow,
+                                                                gs_data));
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+// one relaxation launch over a selection
+static int relax_launch(const double *data, const int32_t *indices, const int32_t *indptr,
+                        const double *dinv, int32_t b, const double *rhs, const double *x_in,
+                        double *x_out, double omega, Sel sel, const int32_t *skip, cudaStream_t st) {
+    if (sel.count <= 0) return 0;
+    DGB_DISPATCH_B(b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+                          data, indices, indptr, dinv, rhs, x_in, x_out, nullptr, omega, sel, skip));
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+static int wavefront_pass(const double *data, const int32_t *indices, const int32_t *indptr,
+                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
+                          double *x, double omega, int direction, const int32_t *skip,
+                          cudaStream_t st) {
+    const int ndiag = Ni + Nj - 1;
+    for (int k = 0; k < ndiag; ++k) {
+        const int c = direction > 0 ? k : ndiag - 1 - k;
+        const int i_lo = c - (Nj - 1) > 0 ? c - (Nj - 1) : 0;
+        const int i_hi = c < Ni - 1 ? c : Ni - 1;
+        Sel sel{2, c, Ni, Nj, i_lo, i_hi - i_lo + 1};
+        int rc = relax_launch(data, indices, indptr, dinv, b, rhs, x, x, omega, sel, skip, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int dgb_block_gs_pass(const double *data, const int32_t *indices, const int32_t *indptr,
+                      const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
+                      double *x, int32_t direction, int32_t mode, const int32_t *skip,
+                      void *stream) {
+    DGB_ARG(data && indices && indptr && dinv && rhs && x && Ni > 0 && Nj > 0);
+    DGB_ARG(direction == 1 || direction == -1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == DGB_GS_REDBLACK) {
+        for (int k = 0; k < 2; ++k) {
+            const int colour = direction > 0 ? k : 1 - k;
+            Sel sel{1, colour, Ni, Nj, 0, Ni * Nj};
+            int rc = relax_launch(data, indices, indptr, dinv, b, rhs, x, x, 1.0, sel, skip, st);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    return wavefront_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, x, 1.0, direction, skip, st);
+}
+
+int dgb_block_relax_sweep(const double *data, const int32_t *indices, const int32_t *indptr,
+                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b,
+                          const double *rhs, const double *x_in, double *x_out, double omega,
+                          void *stream) {
+    DGB_ARG(data && indices && indptr && dinv && rhs && x_in && x_out && Ni > 0 && Nj > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_in == x_out)
+        return wavefront_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, x_out, omega, +1, nullptr, st);
+    Sel sel{0, 0, Ni, Nj, 0, Ni * Nj};
+    return relax_launch(data, indices, indptr, dinv, b, rhs, x_in, x_out, omega, sel, nullptr, st);
+}
+
+int dgb_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream) {
+    DGB_ARG(ctl && sumsq && n > 0);
+    k_smoother_begin<<<1, 1, 0, (cudaStream_t)stream>>>(ctl, sumsq, (double)n);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+int dgb_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream) {
+    DGB_ARG(ctl && sumsq && n > 0);
+    k_smoother_check<<<1, 1, 0, (cudaStream_t)stream>>>(ctl, sumsq, (double)n);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_block_gauss_seidel_pyamg(const double *data, const int32_t *indices,
+                                 const int32_t *indptr, const double *dinv, int32_t Ni,
+                                 int32_t Nj, int32_t b, const double *rhs, double *u,
+                                 int32_t direction, int32_t max_iterations, int32_t mode,
+                                 int32_t check_residual, dgb_smoother_ctl *ctl, double *partials,
+                                 double *sumsq, void *stream) {
+    DGB_ARG(ctl && partials && sumsq);
+    DGB_ARG(direction == 0 || direction == 1 || direction == -1);
+    const int32_t N = Ni * Nj;
+    const int64_t n = (int64_t)N * b;
+    int rc;
+    if (check_residual) {
+        rc = dgb_bsr_residual(data, indices, indptr, N, b, rhs, u, nullptr, partials, sumsq, stream);
+        if (rc) return rc;
+        rc = dgb_smoother_begin(ctl, sumsq, n, stream);
+        if (rc) return rc;
+    }
+    const int32_t *skip = check_residual ? &ctl->skip : nullptr;
+    for (int it = 0; it < max_iterations; ++it) {
+        if (direction >= 0) {
+            rc = dgb_block_gs_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, u, +1, mode, skip, stream);
+            if (rc) return rc;
+        }
+        if (direction <= 0) {
+            rc = dgb_block_gs_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, u, -1, mode, skip, stream);
+            if (rc) return rc;
+        }
+        if (check_residual) {
+            rc = dgb_bsr_residual_skip(data, indices, indptr, N, b, rhs, u, nullptr, partials, sumsq,
+                                       skip, stream);
+            if (rc) return rc;
+            rc = dgb_smoother_check(ctl, sumsq, n, stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int dgb_restrict(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c,
+                 int32_t Nj_c, const double *fine, double *coarse, void *stream) {
+    DGB_ARG(R && fine && coarse && nc > 0 && nf > 0 && Ni_c > 0 && Nj_c > 0);
+    DGB_ARG(kind == DGB_TRANSFER_P || (kind == DGB_TRANSFER_H && nf % 4 == 0));
+    const int64_t nel = (int64_t)Ni_c * Nj_c;
+    int64_t g = (nel * nc + 255) / 256;
+    if (g > sm_count() * 16) g = sm_count() * 16;
+    k_restrict<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, R, nc, nf, Nj_c, nel,
+                                                                              fine, coarse);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_prolong_add(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c,
+                    int32_t Nj_c, const double *coarse, double *fine, void *stream) {
+    DGB_ARG(P && fine && coarse && nc > 0 && nf > 0 && Ni_c > 0 && Nj_c > 0);
+    DGB_ARG(kind == DGB_TRANSFER_P || (kind == DGB_TRANSFER_H && nf % 4 == 0));
+    const int64_t nel = (int64_t)Ni_c * Nj_c;
+    int64_t g = (nel * nf + 255) / 256;
+    if (g > sm_count() * 16) g = sm_count() * 16;
+    k_prolong_add<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, P, nc, nf, Nj_c,
+                                                                                 nel, coarse, fine);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+"""Solver: multigrid / smoother drivers on the device.
+
+Same surface as dgfem/solver.py:13-207 -- attributes grids, restriction_operators,
+prolongation_operators, multigrid_type, residuals; methods solve(), solve_multigrid(levels,
+RHS, u, tol, max_cycles), multigrid_V_cycle(k, RHS, u), solve_smoother(grid, RHS).
+
+One V-cycle is a single call into libdgb200 (dgb_vcycle): every kernel of the cycle is enqueued
+on the current stream with no host synchronisation; the smoother's early-exit state lives in
+device memory.  The only host round trip of solve_multigrid is the one scalar per cycle the
+convergence test needs (dgfem/solver.py:119-123).
+"""
+import ctypes
+import os
+import pickle
+
+import numpy as np
+
+from . import _lib
+from .relaxation import Relaxation, _to_device
+from .timer import Timer
+
+
+def compute_Lp_norm(delta, p):
+    """utils/helpers.py:16-26 (an RMS-type norm: (sum|d|^p / n)^(1/p))."""
+    return (np.sum(abs(delta) ** p) / delta.size) ** (1 / p)
+
+
+class Solver:
+    def __init__(self, method, settings):
+        self.settings = settings
+        self.method = method
+        self.grids = []
+        self.restriction_operators = []
+        self.prolongation_operators = []
+        self.multigrid_type = []
+        self.residuals = []
+        self._hier = None
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------------
+    def solve(self):
+        reference_grid = self.grids[-1]
+        with Timer() as timer:
+            if self.method == "smoother":
+                u = self.solve_smoother(reference_grid, reference_grid.RHS)
+            elif self.method == "multigrid":
+                RHS_0 = reference_grid.RHS
+                u_0 = np.zeros_like(RHS_0)
+                mg = self.settings.solver.multigrid
+                u = self.solve_multigrid(levels=len(self.grids), RHS=RHS_0, u=u_0, tol=mg.tolerance,
+                                         max_cycles=mg.max_cycles)
+            else:
+                raise NotImplementedError(
+                    f"solver method '{self.method}' is outside the B200 hot path (SURVEY.md section 2.1 row 10); "
+                    "use -m or -s")
+        self.timings["solve"] = timer.elapsed()
+        return u
+
+    def solve_smoother(self, grid, RHS):
+        """dgfem/solver.py:61-66."""
+        name = self.settings.solver.smoother
+        return getattr(Relaxation, name)(grid, RHS, max_iterations=100, direction="symmetric")
+
+    # ------------------------------------------------------------------------------------
+    def _smoother_block(self, kind):
+        return getattr(self.settings.solver.multigrid, f"{kind}_coarsening")
+
+    def _build_hierarchy(self):
+        """Device level descriptors (dgb_level) for the current grids / transfer operators."""
+        torch = _lib.require_cuda()
+        n = len(self.grids)
+        levels = (_lib.Level * n)()
+        vecs, ops = [], []
+        s = self.settings
+        gs_mode = s.get("solver.b200.gs_mode", "lexicographic")
+        chk = s.get("solver.b200.check_residual", True)
+        for k, g in enumerate(self.grids):
+            b = g.d_data.shape[1]
+            N = g.Ni * g.Nj
+            if g.d_dinv is None:
+                from .discrete_system import prepare_smoother_data
+                prepare_smoother_data(g)
+            rhs = torch.zeros(N * b, dtype=torch.float64, device="cuda")
+            u = torch.zeros(N * b, dtype=torch.float64, device="cuda")
+            r = torch.zeros(N * b, dtype=torch.float64, device="cuda")
+            vecs.append((rhs, u, r))
+            L = levels[k]
+            L.Ni, L.Nj, L.b, L.nnzb = g.Ni, g.Nj, b, int(g.d_indices.numel())
+            L.data, L.indices, L.indptr, L.dinv = (g.d_data.data_ptr(), g.d_indices.data_ptr(),
+                                                   g.d_indptr.data_ptr(), g.d_dinv.data_ptr())
+            L.rhs, L.u, L.r = rhs.data_ptr(), u.data_ptr(), r.data_ptr()
+            # smoother settings come from the coarsening that links this level to the next coarser
+            # one; the coarsest level uses the first link's (dgfem/solver.py:143,202)
+            kind = self.multigrid_type[k - 1] if k > 0 else (self.multigrid_type[0] if self.multigrid_type else "polynomial")
+            blk = self._smoother_block(kind)
+            pre, post = blk.pre_smoother, blk.post_smoother
+            if pre.smoother != post.smoother or pre.direction != post.direction:
+                raise NotImplementedError("pre and post smoother of a coarsening must be the same smoother/direction")
+            if pre.smoother not in _lib.SMOOTHER_IDS:
+                raise AttributeError(f"Relaxation has no accelerated smoother '{pre.smoother}'")
+            L.smoother = _lib.SMOOTHER_IDS[pre.smoother]
+            L.direction = {"symmetric": 0, "forward": 1, "backward": -1}[pre.direction]
+            L.pre_iterations, L.post_iterations = int(pre.iterations), int(post.iterations)
+            L.omega = float(pre.relaxation_factor)
+            if k < n - 1:
+                R = torch.from_numpy(np.ascontiguousarray(self.restriction_operators[k], dtype=np.float64)).cuda()
+                P = torch.from_numpy(np.ascontiguousarray(self.prolongation_operators[k], dtype=np.float64)).cuda()
+                ops.append((R, P))
+                L.R, L.P = R.data_ptr(), P.data_ptr()
+                L.nc, L.nf = int(R.shape[0]), int(R.shape[1])
+                kind_up = self.multigrid_type[k]
+                if kind_up == "geometric":
+                    if s.solver.multigrid.geometric_coarsening.use_FVM:
+                        raise NotImplementedError("FVM coarse levels are out of scope (SURVEY.md section 2.1 row 19)")
+                    L.transfer_kind = _lib.TRANSFER_H
+                elif kind_up == "polynomial":
+                    L.transfer_kind = _lib.TRANSFER_P
+                else:
+                    raise NotImplementedError(f"multigrid type '{kind_up}' is out of scope")
+        if s.solver.multigrid.coarse_grid_solver != "smoother":
+            raise NotImplementedError("only `coarse grid solver: smoother` runs on the device "
+                                      "(paramfile.yml:23; SURVEY.md section 8f-4)")
+        opts = _lib.VcycleOpts(gs_mode=_lib.GS_REDBLACK if gs_mode == "redblack" else _lib.GS_LEXICOGRAPHIC,
+                               check_residual=1 if chk else 0, coarse_iterations=10, reserved=0)
+        ctl = torch.zeros(32 * n, dtype=torch.uint8, device="cuda")
+        partials = torch.zeros(_lib.load().dgb_partials_len(), dtype=torch.float64, device="cuda")
+        sumsq = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self._hier = dict(levels=levels, n=n, vecs=vecs, ops=ops, opts=opts, ctl=ctl, partials=partials, sumsq=sumsq,
+                          grids=list(self.grids))
+        return self._hier
+
+    def hierarchy(self):
+        if self._hier is None or self._hier["grids"] != list(self.grids):
+            self._build_hierarchy()
+        return self._hier
+
+    def _vcycle_device(self, k):
+        H = self.hierarchy()
+        L = _lib.load()
+        rc = L.dgb_vcycle(H["levels"], k, ctypes.byref(H["opts"]), H["ctl"].data_ptr(), H["partials"].data_ptr(),
+                          H["sumsq"].data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "dgb_vcycle")
+
+    def _check_divergence(self):
+        H = self.hierarchy()
+        raw = H["ctl"].cpu().numpy().tobytes()
+        for k in range(H["n"]):
+            c = _lib.SmootherCtl.from_buffer_copy(raw[32 * k:32 * (k + 1)])
+            if c.diverged:
+                print(f"diverging, residual={c.ratio:.6e}")          # dgfem/relaxation.py:214-216
+                raise SystemExit()
+
+    @staticmethod
+    def _load(dst, src):
+        """Copy a host (NumPy / CPU tensor, ideally pinned) or device vector into a level buffer;
+        returns True when the source lives on the host."""
+        torch = _lib.require_cuda()
+        if isinstance(src, np.ndarray):
+            src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float64))
+        dst.copy_(src, non_blocking=True)
+        return not src.is_cuda
+
+    def multigrid_V_cycle(self, k, RHS, u, out=None):
+        """dgfem/solver.py:141-207.  RHS/u: host vectors (NumPy arrays or CPU tensors; copied to the
+        device and the result copied back) or CUDA tensors (everything stays on the device).
+        `out`: optional host buffer (pinned CPU tensor / NumPy array) that receives the result."""
+        torch = _lib.require_cuda()
+        H = self.hierarchy()
+        rhs_k, u_k, _ = H["vecs"][k - 1]
+        host = self._load(rhs_k, RHS)
+        self._load(u_k, u)
+        self._vcycle_device(k)
+        if host:
+            if out is not None:
+                out_t = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
+                out_t.copy_(u_k, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self._check_divergence()
+                return out
+            res = u_k.cpu().numpy()
+            self._check_divergence()
+            return res
+        return u_k.clone()
+
+    def solve_multigrid(self, levels, RHS, u, tol=1e-6, max_cycles=100):
+        """dgfem/solver.py:114-139."""
+        torch = _lib.require_cuda()
+        H = self.hierarchy()
+        fine = self.grids[-1]
+        rhs_k, u_k, r_k = H["vecs"][levels - 1]
+        host = self._load(rhs_k, RHS)
+        self._load(u_k, u)
+        fine_rhs = fine.d_rhs
+        b = fine.d_data.shape[1]
+        nrow = fine.d_indptr.numel() - 1
+        n_dof = float(nrow * b)
+        st = _lib.stream_ptr()
+
+        def rms():
+            _lib.call("dgb_bsr_residual", fine.d_data, fine.d_indices, fine.d_indptr, nrow, b, fine_rhs, u_k, None,
+                      H["partials"], H["sumsq"], st)
+            return float(np.sqrt(H["sumsq"].item() / n_dof))
+        n = 0
+        residual_0 = rms()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            while n < max_cycles:
+                residual = np.float64(rms()) / np.float64(residual_0)
+                self.residuals.append(float(residual))
+                if residual < tol or np.isnan(residual) or np.isinf(residual):
+                    break
+                self._vcycle_device(levels)
+                n += 1
+        self._check_divergence()
+        self._pickle_residuals(fine)
+        return u_k.cpu().numpy() if host else u_k.clone()
+
+    def _pickle_residuals(self, grid):
+        """dgfem/solver.py:128-138 (the residual history is an observable output)."""
+        try:
+            path = os.path.join(os.getcwd(), "postprocessing", "pickles", "multigrid")
+            os.makedirs(path, exist_ok=True)
+            name = f"residuals_{self.settings.problem.type}_{grid.Ni}X{grid.Nj}_nPoly{grid.P_grid}"
+            name += "_" + "_".join(sorted(set(self.multigrid_type)))
+            name += "_circle" if self.settings.grid.circular else "_rectangle"
+            with open(os.path.join(path, name + ".pkl"), "wb") as f:
+                pickle.dump(self.residuals, f)
+        except OSError:
+            pass

@@ -1,0 +1,261 @@
+/*
+ * dgb200.h -- C ABI of libdgb200.so: the B200-native (sm_100a) implementation of the
+ * dgfem hot path (DG Poisson/Stokes assembly + multigrid V-cycle).
+ *
+ * The reference (thmsdelange/dg-multigrid-solver, pure Python) has no FFI; its hot path
+ * sits behind Python-level seams.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree) -- the
+ * ctypes stub a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name starts with `h_`;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising, unless documented otherwise;
+ *   - return value: 0 = ok, <0 = CUDA/launch error (dgb_last_error() has the text),
+ *     >0 = argument error;
+ *   - all reals are IEEE fp64, all indices int32 (scipy's default index type, which the
+ *     reference's sp.bsr_array uses);
+ *   - BSR layout is scipy's: data[nnzb][b][b] row-major blocks, indices[nnzb] ascending
+ *     within a row, indptr[n_brow+1]   (dgfem/discrete_system.py:145);
+ *   - element numbering m = j*Ni + i (utils/helpers.py:3-14), mode numbering
+ *     n = j_s*(p+1)+i_r, point numbering i_r + N_int*i_s (dgfem/interpolation.py:133-140).
+ */
+#ifndef DGB200_H
+#define DGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGB_ABI_VERSION 1
+
+/* ---- status ------------------------------------------------------------------------- */
+int dgb_abi_version(void);
+const char *dgb_last_error(void);
+/* number of SMs of the current device (used by callers to size workspaces) */
+int dgb_sm_count(void);
+
+/* Number of doubles a `partials` workspace must hold (per-CTA partial sums of the fused
+ * norm reductions; reduced in a fixed order => bitwise reproducible norms). */
+int dgb_partials_len(void);
+
+/* Kernels launched by this library since the last reset (bench.py's gpu_launches). */
+long long dgb_launch_count(int32_t reset);
+
+/* ---- device-side smoother control block ------------------------------------------------
+ * Carries the early-exit / divergence state of Relaxation.block_gauss_seidel_pyamg
+ * (dgfem/relaxation.py:202-216) on the device, so a smoother call needs no host sync:
+ * once `skip` is set the remaining sweeps of that call are no-ops. */
+typedef struct dgb_smoother_ctl {
+    double res0;      /* RMS residual at smoother entry            (relaxation.py:202) */
+    double ratio;     /* last normalised residual                  (relaxation.py:208) */
+    int32_t skip;     /* ratio < 1e-6 seen -> stop sweeping        (relaxation.py:211-213) */
+    int32_t diverged; /* ratio > 1e10 seen -> caller raises/exits  (relaxation.py:214-216) */
+    int32_t iters;    /* completed iterations of this call */
+    int32_t calls;    /* smoother calls since the block was zeroed */
+} dgb_smoother_ctl;
+
+/* ---- K5: block-sparse operator apply / residual ---------------------------------------
+ * replaces  grid.BSR @ u  (scipy bsr_matvec) -- dgfem/solver.py:117,119,150;
+ *           dgfem/relaxation.py:202,208; utils/helpers.py:39 */
+int dgb_bsr_apply(const double *data, const int32_t *indices, const int32_t *indptr,
+                  int32_t n_brow, int32_t b, const double *x, double *y, void *stream);
+
+/* r = rhs - A x (r may be NULL: norm only) and sum(r^2) into *sumsq (device scalar),
+ * replaces  RHS - grid.BSR @ u  + compute_Lp_norm(.,2)  (utils/helpers.py:16-39).
+ * `partials` is a workspace of dgb_partials_len() doubles. */
+int dgb_bsr_residual(const double *data, const int32_t *indices, const int32_t *indptr,
+                     int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
+                     double *partials, double *sumsq, void *stream);
+
+/* Same, gated by an optional device flag (dgb_smoother_ctl.skip): a no-op when *skip != 0. */
+int dgb_bsr_residual_skip(const double *data, const int32_t *indices, const int32_t *indptr,
+                          int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
+                          double *partials, double *sumsq, const int32_t *skip, void *stream);
+
+/* sum(v^2) of a plain vector into *sumsq (device scalar). */
+int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream);
+
+/* ---- K6: batched inverse of the diagonal blocks ---------------------------------------
+ * replaces  pyamg.util.utils.get_block_diag(A, blocksize, inv_flag=True)
+ *           (dgfem/pyamg_relaxation.py:230-231; recomputed per call there, once here)
+ * and the per-row np.linalg.solve(D_i, .) of dgfem/relaxation.py:148,194.
+ * dinv[n_brow][b][b]; *info (device int) is set to 1+row of the first singular block. */
+int dgb_block_diag_inverse(const double *data, const int32_t *indices, const int32_t *indptr,
+                           int32_t n_brow, int32_t b, double *dinv, int32_t *info, void *stream);
+
+/* Build the smoother stream: a copy of `data` with every diagonal block replaced by its
+ * inverse (so one directional pass streams exactly nnzb blocks). */
+int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_t *indptr,
+                        const double *dinv, int32_t n_brow, int32_t b, double *gs_data,
+                        void *stream);
+
+/* ---- K7: block Gauss-Seidel, one directional pass ---------------------------------------
+ * replaces  pyamg.amg_core.block_gauss_seidel(Ap,Aj,Ax,x,b,Dinv,row_start,row_stop,row_step,bs)
+ *           (dgfem/pyamg_relaxation.py:252-255).
+ * direction: +1 forward (rows 0..N-1), -1 backward (rows N-1..0).
+ * mode: DGB_GS_LEXICOGRAPHIC reproduces the lexicographic order exactly through the
+ *       anti-diagonal wavefront c=i+j of the Ni x Nj element grid (requires the 5-point
+ *       block stencil the DG operator has); DGB_GS_REDBLACK is the 2-colour multicolour
+ *       variant (forward = colour 0 then 1, backward = 1 then 0).
+ * skip: optional device flag (ctl->skip); when non-zero the pass is a no-op. */
+#define DGB_GS_LEXICOGRAPHIC 0
+#define DGB_GS_REDBLACK 1
+int dgb_block_gs_pass(const double *data, const int32_t *indices, const int32_t *indptr,
+                      const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
+                      double *x, int32_t direction, int32_t mode, const int32_t *skip,
+                      void *stream);
+
+/* ---- K8: one block-row relaxation sweep, x_out_i = omega*Dinv_i(rhs_i - sum_{j!=i} A_ij x_in_j)
+ *                                                   + (1-omega) x_in_i
+ * x_out != x_in : block-Jacobi            (first iteration of dgfem/relaxation.py:123-150)
+ * x_out == x_in : forward block-GS, lexicographic wavefront (dgfem/relaxation.py:170-195 and
+ *                 iterations >= 2 of block_jacobi, whose `u = u_new` aliases the buffers). */
+int dgb_block_relax_sweep(const double *data, const int32_t *indices, const int32_t *indptr,
+                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b,
+                          const double *rhs, const double *x_in, double *x_out, double omega,
+                          void *stream);
+
+/* ---- smoother control ------------------------------------------------------------------ */
+/* ctl->res0 = sqrt(*sumsq / n); skip = diverged = iters = 0; calls += 1 */
+int dgb_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream);
+/* ratio = sqrt(*sumsq / n) / res0; apply the 1e-6 / 1e10 tests; iters += 1 (unless skipped) */
+int dgb_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream);
+
+/* Whole smoother call on the device:
+ * replaces  Relaxation.block_gauss_seidel_pyamg(grid, RHS, u, direction, omega, max_iterations)
+ *           (dgfem/relaxation.py:198-218); u is updated IN PLACE (the host wrapper copies).
+ * direction: 0 symmetric, +1 forward, -1 backward.  `check_residual` = 0 drops the
+ * per-iteration residual norms (and with them the early exit) -- NOT reference semantics. */
+int dgb_block_gauss_seidel_pyamg(const double *data, const int32_t *indices,
+                                 const int32_t *indptr, const double *dinv, int32_t Ni,
+                                 int32_t Nj, int32_t b, const double *rhs, double *u,
+                                 int32_t direction, int32_t max_iterations, int32_t mode,
+                                 int32_t check_residual, dgb_smoother_ctl *ctl, double *partials,
+                                 double *sumsq, void *stream);
+
+/* ---- K9: level transfer ----------------------------------------------------------------
+ * replaces the einsum('ij,kj->ki', R|P, .) transfers of Solver.multigrid_V_cycle
+ * (dgfem/solver.py:152-193) with the dense operators built in
+ * DGFEM.assemble_multigrid_operators (dgfem/dgfem.py:303-372).
+ * kind: DGB_TRANSFER_P  per-element  coarse[e] = R[nc x nf] fine[e]
+ *       DGB_TRANSFER_H  2x2 children gathered with the reference's reshape/transpose
+ *                       (solver.py:164): R is [b x 4b], Ni_c x Nj_c coarse elements.
+ * restrict: coarse = R * gather(fine);  prolong_add: fine += scatter(P * coarse). */
+#define DGB_TRANSFER_P 1
+#define DGB_TRANSFER_H 2
+int dgb_restrict(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c,
+                 int32_t Nj_c, const double *fine, double *coarse, void *stream);
+int dgb_prolong_add(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c,
+                    int32_t Nj_c, const double *coarse, double *fine, void *stream);
+
+/* ---- V-cycle driver ---------------------------------------------------------------------
+ * replaces  Solver.multigrid_V_cycle(k, RHS, u)  (dgfem/solver.py:141-207).
+ * levels[0] is the coarsest grid, levels[nlevels-1] the finest (the order of
+ * Solver.grids); levels[k].R/P map between level k (coarse) and k+1 (fine). */
+typedef struct dgb_level {
+    int32_t Ni, Nj, b, nnzb;
+    const double *data;      /* [nnzb][b][b]                                   */
+    const int32_t *indices;  /* [nnzb]                                         */
+    const int32_t *indptr;   /* [Ni*Nj+1]                                      */
+    const double *dinv;      /* [Ni*Nj][b][b]                                  */
+    double *rhs;             /* [Ni*Nj*b] work: right-hand side of this level  */
+    double *u;               /* [Ni*Nj*b] work: iterate of this level          */
+    double *r;               /* [Ni*Nj*b] work: residual                       */
+    /* transfer between this level (coarse side) and the next finer one */
+    int32_t transfer_kind;   /* 0 on the finest level                          */
+    int32_t nc, nf;          /* R is [nc x nf], P is [nf x nc]                 */
+    const double *R;
+    const double *P;
+    /* smoother settings of the coarsening that owns this level (paramfile.yml:20-65) */
+    int32_t smoother;        /* DGB_SMOOTHER_*                                 */
+    int32_t direction;       /* 0 symmetric, +1 forward, -1 backward           */
+    int32_t pre_iterations, post_iterations;
+    double omega;
+} dgb_level;
+
+#define DGB_SMOOTHER_BLOCK_GS_PYAMG 0
+#define DGB_SMOOTHER_BLOCK_JACOBI 1
+#define DGB_SMOOTHER_BLOCK_GS 2
+
+typedef struct dgb_vcycle_opts {
+    int32_t gs_mode;            /* DGB_GS_LEXICOGRAPHIC | DGB_GS_REDBLACK       */
+    int32_t check_residual;     /* 1 = reference semantics (early exit active)  */
+    int32_t coarse_iterations;  /* 10 in the reference (solver.py:204)          */
+    int32_t reserved;
+} dgb_vcycle_opts;
+
+/* One V-cycle on the finest level: levels[n-1].u is updated in place from levels[n-1].rhs.
+ * ctl: array of nlevels control blocks (device); partials/sumsq: workspaces. */
+int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
+               dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream);
+
+/* ---- K0-K3: DG assembly (Poisson) ------------------------------------------------------- */
+/* Basis / quadrature / geometry-operator tables of one level, uploaded once
+ * (replaces Grid.initialize_interpolation, dgfem/grid.py:178-213).  All arrays are HOST
+ * pointers, row-major; copied into a device-resident table block owned by the returned
+ * handle.  Layout documented in DESIGN.md section "Tables". */
+typedef struct dgb_tables dgb_tables;
+typedef struct dgb_tables_desc {
+    int32_t Pg;      /* geometry degree, ng = (Pg+1)^2 nodes per element          */
+    int32_t p;       /* solution degree, b = (p+1)^2                              */
+    int32_t nq1;     /* N_int (points per direction)                              */
+    int32_t cf;      /* coarsening factor of this level (1 = fine)                */
+    const double *h_V, *h_Vr, *h_Vs;            /* [nq1^2][b] volume tables       */
+    const double *h_w2;                         /* [nq1^2] 2-D weights (r fastest)*/
+    const double *h_w1;                         /* [nq1]                          */
+    const double *h_Vf, *h_Vrf, *h_Vsf;         /* [4][nq1][b] traces: iL,iR,jL,jR*/
+    /* geometry operators: element nodes (F-order) -> x, x_r, x_s at points.
+     * volume: [nq1^2][ng]; faces [4][nq1][ng] in the order imin,imax,jmin,jmax.
+     * For cf > 1 every point also carries the fine sub-element offset it samples
+     * (dgfem/element.py:273-310): sub_vol[nq1^2][2], sub_face[4][nq1][2]. */
+    const double *h_GX, *h_GR, *h_GS;
+    const double *h_FX, *h_FR, *h_FS;
+    const int32_t *h_sub_vol, *h_sub_face;
+} dgb_tables_desc;
+int dgb_tables_create(const dgb_tables_desc *h_desc, dgb_tables **out);
+void dgb_tables_destroy(dgb_tables *t);
+
+/* K0: geometric terms of all Ni x Nj elements of a level
+ * replaces Element.compute_geometric_terms / metric_xy_rs (dgfem/element.py:52-130) and
+ * CoarseElement._init_coarse_element (dgfem/element.py:242-356).
+ * xn, yn: node coordinates in Plot3D file order [jl][il] (i fastest; dgfem/grid.py:49-51),
+ * il = Ni_fine*Pg+1.  Outputs (element-major, m = j*Ni+i):
+ *   vol [N][7][nq]   : J, rx, sx, ry, sy, x, y at the volume points
+ *   face[N][4][8][nq1]: per face (imin,imax,jmin,jmax): J_f, alpha, beta, x, y, nx, ny, 0
+ *                       with alpha = rx*nx+ry*ny, beta = sx*nx+sy*ny (so d_n phi = Vr*alpha+Vs*beta)
+ *   area[N]          : A = sum J w                                   (dgfem/element.py:30) */
+int dgb_metrics(const dgb_tables *t, const double *xn, const double *yn, int32_t il,
+                int32_t Ni, int32_t Nj, double *vol, double *face, double *area, void *stream);
+
+/* K1+K2: assemble the Poisson operator of a level straight into BSR
+ * replaces Poisson.assemble_BSR_Poisson (dgfem/discrete_system.py:54-145) with
+ * Element.compute_momentum_laplace_volume_integral / compute_mass_matrix
+ * (dgfem/element.py:181-199,132-133) and Face.compute_momentum_laplace_SIP_terms
+ * (dgfem/face.py:115-280).  flags: bit0 periodic in i (O-grid), bit1 periodic in j,
+ * bit2 multiply by the inverse mass matrix.
+ * Outputs: indptr[N+1], indices[nnzb], data[nnzb][b][b], minv[N][b][b]. */
+#define DGB_FLAG_PERIODIC_I 1
+#define DGB_FLAG_PERIODIC_J 2
+#define DGB_FLAG_MINV 4
+int64_t dgb_poisson_nnzb(int32_t Ni, int32_t Nj, int32_t flags);
+int dgb_assemble_poisson(const dgb_tables *t, const double *vol, const double *face,
+                         const double *area, int32_t Ni, int32_t Nj, double nu, double sigma,
+                         int32_t flags, int32_t *indptr, int32_t *indices, double *data,
+                         double *minv, void *stream);
+
+/* K3: right-hand side
+ * replaces Poisson.assemble_RHS_Poisson (dgfem/discrete_system.py:355-403).
+ * f_vol[N][nq]: source at the volume points; g_face[N][4][nq1]: Dirichlet data at the
+ * face points (only domain-boundary faces are read). */
+int dgb_assemble_rhs(const dgb_tables *t, const double *vol, const double *face,
+                     const double *area, const double *minv, const double *f_vol,
+                     const double *g_face, int32_t Ni, int32_t Nj, double nu, double sigma,
+                     int32_t flags, double *rhs, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGB200_H */

@@ -1,0 +1,59 @@
+"""CPU tier: the C-ABI library builds/loads and exports every symbol include/dgb200.h declares
+(no compute calls here -- there is no GPU in this tier)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from helpers import REPO
+
+
+def _declared_symbols():
+    src = open(os.path.join(REPO, "include", "dgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dgb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_hot_path():
+    names = _declared_symbols()
+    for must in ("dgb_bsr_apply", "dgb_bsr_residual", "dgb_block_gs_pass", "dgb_block_relax_sweep",
+                 "dgb_block_diag_inverse", "dgb_restrict", "dgb_prolong_add", "dgb_vcycle",
+                 "dgb_metrics", "dgb_assemble_poisson", "dgb_assemble_rhs"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from dg_multigrid_solver_b200 import build
+    lib = build.build_library()
+    L = ctypes.CDLL(lib)
+    for name in _declared_symbols():
+        assert hasattr(L, name), f"{name} declared in include/dgb200.h but not exported"
+    assert L.dgb_abi_version() == 1
+    assert L.dgb_partials_len() >= 1024
+
+
+def test_ctypes_binding_covers_the_header():
+    from dg_multigrid_solver_b200 import _lib
+    assert set(_lib.SIGNATURES) == set(_declared_symbols())
+    assert ctypes.sizeof(_lib.SmootherCtl) == 32
+    _lib.load()
+
+
+def test_product_has_no_cpu_path():
+    """Without a GPU the product refuses to run (no oracle / CPU fallback on the product path)."""
+    import torch
+    from dg_multigrid_solver_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.DgbError):
+        _lib.require_cuda()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "dg_multigrid_solver_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "dgoracle" not in txt and "oracle/" not in txt, f

@@ -1,0 +1,113 @@
+"""CPU tier: host-side logic of the product package (settings, tables, Plot3D, CLI, hierarchy
+bookkeeping) -- everything that does not need a device."""
+import numpy as np
+import pytest
+
+from helpers import CASES, GRIDS, base_params, golden, grid_path, make_settings
+
+
+def test_settings_attribute_view_and_updates():
+    from dg_multigrid_solver_b200.settings import Settings
+    s = Settings(base_params())
+    assert s.grid.polynomial_degree == 5 and s.grid.O_grid is False
+    assert s.solver.multigrid.polynomial_coarsening.pre_smoother.smoother == "block_gauss_seidel_pyamg"
+    assert s.solution.u.integration_polynomial_degree_factor == 3
+    s.update_settings({"grid_file": "x.xyz", "p_grid": 2, "smoother": "block_jacobi"})
+    assert s.grid.filename == "x.xyz" and s.grid.polynomial_degree == 2
+    assert s.solver.smoother == "block_jacobi" and s.solver.discretization == "dg"
+    s.update_setting("solver.method", "multigrid")
+    assert s.solver.method == "multigrid"
+    assert s.get("solver.b200.gs_mode") == "lexicographic"
+    assert s.get("solver.nothing.here", 7) == 7
+
+
+def test_tables_match_oracle_tables():
+    from dg_multigrid_solver_b200.tables import Tables, h_restriction, p_restriction
+    from dgoracle import multigrid as om
+    from dgoracle import tables as ot
+    for Pg, p in [(1, 1), (2, 1), (2, 2), (5, 3), (5, 5)]:
+        T, O = Tables(Pg, p), ot.LevelTables(Pg, p)
+        assert T.nq1 == O.N_int and T.b == O.b
+        assert np.array_equal(T.V, O.V_DOF_int) and np.array_equal(T.Vr, O.Vr_DOF_int)
+        assert np.array_equal(T.Vs, O.Vs_DOF_int) and np.array_equal(T.w2, np.ravel(O.w_int_2D, order="F"))
+        for k, nm in enumerate(("iL", "iR", "jL", "jR")):
+            assert np.array_equal(T.Vf[k], O.V_face[nm]) and np.array_equal(T.Vrf[k], O.Vr_face[nm])
+        assert np.allclose(T.GX, O.L_int, rtol=0, atol=1e-14)
+        assert np.allclose(T.GR, O.Dr_int @ O.L_gg, rtol=0, atol=1e-13)
+        for k, f in enumerate(("imin", "imax", "jmin", "jmax")):
+            assert np.allclose(T.FS[k], O.Ds_face[f] @ O.L_gg, rtol=0, atol=1e-13)
+        assert np.array_equal(T.V_DOF_grid, O.V_DOF_grid)
+    for pc, pf in [(1, 2), (1, 3), (3, 5), (0, 1), (2, 5)]:
+        assert np.array_equal(p_restriction(pc, pf), om.p_restriction(pc, pf))
+    assert np.array_equal(h_restriction()[0], om.h_restriction()[0])
+    g = golden("c2")
+    assert np.array_equal(h_restriction()[0], g["R0"]) and np.array_equal(p_restriction(3, 5), g["R2"])
+
+
+def test_coarse_tables_follow_reference_point_location():
+    """cf = 2, 4, 8: sub-element offsets and local coordinates (element.py:273-310, App. B.12)."""
+    from dg_multigrid_solver_b200.tables import Tables
+    from dgoracle import geometry as og
+    from dgoracle import tables as ot
+    for cf in (2, 4, 8):
+        T, O = Tables(2, 1, cf=cf), ot.LevelTables(2, 1)
+        for (iR, iS, m, n, r, s) in og.coarse_point_map(O, cf):
+            q = iR + T.nq1 * iS
+            assert tuple(T.sub_vol[q]) == (m, n)
+            L, Dr, Ds = O.point_ops(r, s)
+            assert np.allclose(T.GX[q], L[0], atol=1e-14)
+            assert np.allclose(T.GR[q], cf * (Dr @ O.L_gg)[0], atol=1e-12)
+        # B.12: for cf >= 8 the "imin" face is sampled from an interior fine element
+        assert T.sub_face[0, 0, 0] == (0 if cf <= 4 else 1)
+
+
+def test_plot3d_reader_matches_oracle_reader():
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dgoracle import plot3d
+    for name in ("c1", "c2"):
+        case = CASES[name]
+        geo = Geometry(grid_path(case), make_settings(case))
+        x, y, Ni, Nj = plot3d.read_plot3d(grid_path(case), case["pg"])
+        assert (geo.Ni, geo.Nj) == (Ni, Nj)
+        assert np.array_equal(geo.x, x) and np.array_equal(geo.y, y)
+        assert geo.xn.shape == (geo.jl, geo.il) and geo.xn[1, 2] == x[2, 1]
+
+
+def test_plot3d_rejects_open_o_grid():
+    from dg_multigrid_solver_b200.grid import Geometry
+    case = dict(CASES["c1"], ogrid=True)
+    with pytest.raises(ValueError):
+        Geometry(grid_path(CASES["c1"]), make_settings(case))
+
+
+def test_synthetic_grid_rules_reproduce_shipped_files():
+    from dgoracle import plot3d
+    x, y, Ni, Nj = plot3d.read_plot3d(f"{GRIDS}/Rectangle_8X8_nPoly2.xyz", 2)
+    xs, ys = plot3d.rectangle_nodes(Ni, Nj, 2)
+    assert np.array_equal(x, xs) and np.array_equal(y, ys)          # byte-identical rule
+    x, y, Ni, Nj = plot3d.read_plot3d(f"{GRIDS}/CircleInCircle_8X8_nPoly5.xyz", 5)
+    xs, ys = plot3d.circle_in_circle_nodes(Ni, Nj, 5)
+    assert np.abs(x - xs).max() < 5e-16 and np.abs(y - ys).max() < 5e-16
+
+
+def test_cli_parser_matches_reference_flags():
+    from dg_multigrid_solver_b200.__main__ import build_parser
+    p = build_parser()
+    a = p.parse_args(["-m"])
+    assert a.solve_multigrid and not a.solve_smoother
+    a = p.parse_args(["-s", "--smoother", "block_jacobi", "-f", "g.xyz", "--p-grid", "2", "-v"])
+    assert a.solve_smoother and a.smoother == "block_jacobi" and a.grid_file == "g.xyz" and a.p_grid == 2
+    with pytest.raises(SystemExit):
+        p.parse_args(["-m", "-d"])                                # mutually exclusive solver flags
+    with pytest.raises(SystemExit):
+        p.parse_args([])                                          # one solver flag is required
+
+
+def test_mms_fields_host():
+    from dg_multigrid_solver_b200.mms import PoissonMMS
+    from dgoracle.mms import PoissonMMS as OMMS
+    s = make_settings(CASES["c1"])
+    m, o = PoissonMMS(s), OMMS(s.problem.exact_solution.u, 1.0)
+    X, Y = np.meshgrid(np.linspace(-1, 1, 7), np.linspace(-1, 1, 5))
+    assert np.array_equal(m.solution(X, Y), o.solution(X, Y))
+    assert np.array_equal(m.source(X, Y), o.source(X, Y))
