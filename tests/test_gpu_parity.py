@@ -76,7 +76,9 @@ def test_vcycle_and_residual_history(mg):
     assert np.allclose(hist, g["residuals"], rtol=HIST_RTOL, atol=HIST_ATOL)
     assert abs(d.L2_error_u - float(g["L2_error"])) < 1e-9 * max(1.0, float(g["L2_error"]))
     assert abs(d.L1_error_u - float(g["L1_error"])) < 1e-9 * max(1.0, float(g["L1_error"]))
-    assert abs(d.residual - float(g["final_residual"])) < 1e-9 * abs(float(g["final_residual"])) + 1e-13
+    # the final residual sits ~1e-7 below the initial one: same rounding floor as the history's tail
+    res0 = np.sqrt(np.mean(fine.RHS ** 2))
+    assert abs(d.residual - float(g["final_residual"])) < HIST_ATOL * res0 + HIST_RTOL * float(g["final_residual"])
 
 
 @pytest.mark.parametrize("name", ["smooth_rect4_p2", "smooth_circ4_p5"])
@@ -114,7 +116,10 @@ def test_block_diag_inverse_and_transfers():
         info = torch.zeros(1, dtype=torch.int32, device="cuda")
         _lib.call("dgb_block_diag_inverse", data, indices, indptr, N, b, dinv, info, _lib.stream_ptr())
         assert int(info.item()) == 0
-        assert np.abs(dinv.cpu().numpy() - np.linalg.inv(blocks)).max() < 1e-11
+        ref = np.linalg.inv(blocks)
+        err = np.abs(dinv.cpu().numpy() - ref).max(axis=(1, 2)) / np.abs(ref).max(axis=(1, 2))
+        cond = np.linalg.cond(blocks)
+        assert np.all(err < 1e-14 * cond + 1e-13)          # backward-stable up to the block's conditioning
     # singular block is flagged (the reference's pinv would silently pseudo-invert)
     blocks = rng.standard_normal((3, 4, 4)); blocks[1] = 0.0
     data = torch.from_numpy(blocks).cuda()
