@@ -276,13 +276,12 @@ def run_b200(args):
             fn()
         c.record(); torch.cuda.synchronize()
         return a.elapsed_time(c) / reps, int(L.dgb_launch_count(0)) // reps
-    k_apply = timed(lambda: _lib.call("dgb_bsr_apply", fine.d_data, fine.d_indices, fine.d_indptr, N, b, u_k, y, st))
-    k_resid = timed(lambda: _lib.call("dgb_bsr_residual", fine.d_data, fine.d_indices, fine.d_indptr, N, b,
-                                      fine.d_rhs, u_k, None, ws_part, ws_sum, st))
+    op = fine.operator()
+    k_apply = timed(lambda: _lib.call("dgb_bsr_apply", op, u_k, y, st))
+    k_resid = timed(lambda: _lib.call("dgb_bsr_residual", op, fine.d_rhs, u_k, None, ws_part, ws_sum, None, st))
     mode = _lib.GS_REDBLACK if args.gs_mode == "redblack" else _lib.GS_LEXICOGRAPHIC
     xg = u_k.clone()
-    k_gs = timed(lambda: _lib.call("dgb_block_gs_pass", fine.d_data, fine.d_indices, fine.d_indptr, fine.d_dinv,
-                                   fine.Ni, fine.Nj, b, fine.d_rhs, xg, 1, mode, None, st), reps=3)
+    k_gs = timed(lambda: _lib.call("dgb_block_gs_pass", op, fine.d_rhs, xg, 1, mode, None, st), reps=3)
     peak, peak_src = measured_peak()
     kern = {}
     for nm, (ms, nl), nbytes in (("apply", k_apply, ab["apply"]), ("residual_norm", k_resid, ab["residual"]),

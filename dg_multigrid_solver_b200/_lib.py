@@ -25,12 +25,18 @@ class SmootherCtl(ctypes.Structure):
                 ("iters", c_i32), ("calls", c_i32)]
 
 
+class Operator(ctypes.Structure):
+    """dgb_operator (include/dgb200.h): host struct of device pointers."""
+    _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
+                ("stencil", c_i32), ("reserved", c_i32),
+                ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp), ("gs_data", c_vp)]
+
+
 class Level(ctypes.Structure):
     """dgb_level (include/dgb200.h)."""
-    _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
-                ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp),
+    _fields_ = [("op", Operator),
                 ("rhs", c_vp), ("u", c_vp), ("r", c_vp),
-                ("transfer_kind", c_i32), ("nc", c_i32), ("nf", c_i32),
+                ("transfer_kind", c_i32), ("nc", c_i32), ("nf", c_i32), ("pad0", c_i32),
                 ("R", c_vp), ("P", c_vp),
                 ("smoother", c_i32), ("direction", c_i32),
                 ("pre_iterations", c_i32), ("post_iterations", c_i32), ("omega", c_f64)]
@@ -53,24 +59,26 @@ SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_s
 FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV = 1, 2, 4
 
 # name -> (restype, argtypes); every symbol include/dgb200.h declares
+OP = ctypes.POINTER(Operator)
 SIGNATURES = {
     "dgb_abi_version": (c_i32, []),
     "dgb_last_error": (ctypes.c_char_p, []),
     "dgb_sm_count": (c_i32, []),
     "dgb_partials_len": (c_i32, []),
     "dgb_launch_count": (ctypes.c_longlong, [c_i32]),
-    "dgb_bsr_apply": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "dgb_bsr_residual": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "dgb_bsr_residual_skip": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_set_kernel_path": (c_i32, [c_i32]),
+    "dgb_device_error": (c_i32, [c_i32]),
+    "dgb_bsr_apply": (c_i32, [OP, c_vp, c_vp, c_vp]),
+    "dgb_bsr_residual": (c_i32, [OP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dgb_block_diag_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
-    "dgb_block_gs_pass": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
-    "dgb_block_relax_sweep": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_f64, c_vp]),
+    "dgb_check_stencil": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_gs_pass": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_relax_sweep": (c_i32, [OP, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "dgb_smoother_check": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
-    "dgb_block_gauss_seidel_pyamg": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp,
-                                             c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_block_gauss_seidel_pyamg": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_restrict": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_prolong_add": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_vcycle": (c_i32, [ctypes.POINTER(Level), c_i32, ctypes.POINTER(VcycleOpts), c_vp, c_vp, c_vp, c_vp]),
@@ -99,8 +107,10 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.dgb_abi_version() != 1:
+    if L.dgb_abi_version() != 2:
         raise DgbError("libdgb200.so ABI version mismatch")
+    if os.environ.get("DGB_KERNELS", "auto") == "generic":
+        L.dgb_set_kernel_path(1)
     _lib = L
     return L
 
@@ -131,7 +141,9 @@ def call(name, *args):
     L = load()
     conv = []
     for a in args:
-        if hasattr(a, "data_ptr") or isinstance(a, np.ndarray):
+        if isinstance(a, Operator):
+            conv.append(ctypes.byref(a))
+        elif hasattr(a, "data_ptr") or isinstance(a, np.ndarray):
             conv.append(ptr(a))
         else:
             conv.append(a)

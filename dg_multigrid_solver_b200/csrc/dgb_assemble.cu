@@ -13,6 +13,7 @@
 // Every interior face is evaluated once per adjacent element (test side = that element),
 // i.e. only the two blocks that element's row needs -- the reference evaluates all four
 // blocks twice and discards half (discrete_system.py:74-77).
+#include "dgb_async.cuh"
 #include "dgb_common.cuh"
 
 struct dgb_tables {
@@ -127,47 +128,6 @@ k_area(TabView T, const double *__restrict__ vol, int64_t N, double *__restrict_
         double a = 0.0;
         for (int q = 0; q < T.nq; ++q) a = fma(J[q], T.w2[q], a);   // element.py:30
         area[e] = a;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// BSR structure of the 5-point block stencil, closed form (discrete_system.py:83-144)
-struct Stencil {
-    int Ni, Nj, per_i, per_j;
-    __host__ __device__ int bj(int j) const { return per_j ? 0 : ((j == 0) + (j == Nj - 1)); }
-    __host__ __device__ int count(int i, int j) const {
-        return 5 - bj(j) - (per_i ? 0 : ((i == 0) + (i == Ni - 1)));
-    }
-    __host__ __device__ int64_t row_start(int i, int j) const {
-        // blocks in all element rows j' < j, then in (i' < i, j)
-        const int nbrows = per_j ? 0 : ((j > 0) + (j >= Nj));
-        int64_t s = (int64_t)j * (5 * (int64_t)Ni - (per_i ? 0 : 2)) - (int64_t)Ni * nbrows;
-        if (j < Nj) s += (int64_t)i * (5 - bj(j)) - ((per_i || i == 0) ? 0 : 1);
-        return s;
-    }
-    // neighbour element index per slot {m, iL, iR, jL, jR} (-1 = Dirichlet boundary)
-    __host__ __device__ void cols(int i, int j, int c[5]) const {
-        const int m = j * Ni + i;
-        c[0] = m;
-        c[1] = i > 0 ? m - 1 : (per_i ? j * Ni + Ni - 1 : -1);
-        c[2] = i < Ni - 1 ? m + 1 : (per_i ? j * Ni : -1);
-        c[3] = j > 0 ? m - Ni : (per_j ? (Nj - 1) * Ni + i : -1);
-        c[4] = j < Nj - 1 ? m + Ni : (per_j ? i : -1);
-    }
-};
-
-// rank of each present slot in ascending column order; ties keep slot order (python's stable
-// sorted(), discrete_system.py:137-138)
-__device__ __forceinline__ void slot_ranks(const int c[5], int rank[5]) {
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        int rk = 0;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            if (c[t] < 0 || t == s) continue;
-            if (c[t] < c[s] || (c[t] == c[s] && t < s)) ++rk;
-        }
-        rank[s] = c[s] < 0 ? -1 : rk;
     }
 }
 

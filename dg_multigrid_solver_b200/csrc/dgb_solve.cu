@@ -336,6 +336,27 @@ k_prolong_add(int kind, const double *__restrict__ P, int nc, int nf, int Nj_c, 
 
 }  // namespace dgb
 
+namespace dgb {
+// streaming kernels (dgb_stream.cu)
+extern int g_kernel_path;
+bool stream_supported(int b);
+int stream_launch(int mode, int b, const double *data, const int32_t *indices, const int32_t *indptr, int N,
+                  int Ni, const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
+                  int colour, const int32_t *skip, cudaStream_t st, int *grid_out);
+int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, int Ni, int Nj, int flags, int dir,
+                   double omega, const int32_t *skip, cudaStream_t st);
+enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
+
+static bool use_stream(const dgb_operator *op) {
+    return g_kernel_path == 0 && op->stencil >= 0 && stream_supported(op->b);
+}
+static int check_op(const dgb_operator *op) {
+    DGB_ARG(op != nullptr);
+    DGB_ARG(op->data && op->indices && op->indptr && op->Ni > 0 && op->Nj > 0 && op->b > 0);
+    return 0;
+}
+}  // namespace dgb
+
 using namespace dgb;
 
 // =========================================================================================
@@ -353,39 +374,44 @@ long long dgb_launch_count(int32_t reset) {
     return n;
 }
 
-int dgb_bsr_apply(const double *data, const int32_t *indices, const int32_t *indptr,
-                  int32_t n_brow, int32_t b, const double *x, double *y, void *stream) {
-    DGB_ARG(data && indices && indptr && x && y && n_brow >= 0);
-    if (n_brow == 0) return 0;
+int dgb_bsr_apply(const dgb_operator *op, const double *x, double *y, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(x && y);
     cudaStream_t st = (cudaStream_t)stream;
-    Sel sel{0, 0, n_brow, 1, 0, n_brow};
-    DGB_DISPATCH_B(b, k_rows<B, MODE_APPLY><<<rows_grid(n_brow, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
-                          data, indices, indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
+    const int N = op->Ni * op->Nj;
+    if (use_stream(op))
+        return stream_launch(S_APPLY, op->b, op->data, op->indices, op->indptr, N, op->Ni, nullptr, x, y, nullptr,
+                             1.0, -1, nullptr, st, nullptr);
+    Sel sel{0, 0, N, 1, 0, N};
+    DGB_DISPATCH_B(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+                              op->data, op->indices, op->indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
     DGB_LAUNCH_OK();
     return 0;
 }
 
-int dgb_bsr_residual_skip(const double *data, const int32_t *indices, const int32_t *indptr,
-                          int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
-                          double *partials, double *sumsq, const int32_t *skip, void *stream) {
-    DGB_ARG(data && indices && indptr && x && rhs && partials && sumsq && n_brow > 0);
+int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x, double *r,
+                     double *partials, double *sumsq, const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(x && rhs && partials && sumsq);
     cudaStream_t st = (cudaStream_t)stream;
-    Sel sel{0, 0, n_brow, 1, 0, n_brow};
+    const int N = op->Ni * op->Nj;
     int grid = 1;
-    DGB_DISPATCH_B(b, grid = rows_grid(n_brow, RowCfg<B>::EPB);
-                   k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
-                       data, indices, indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
-    DGB_LAUNCH_OK();
+    if (use_stream(op)) {
+        rc = stream_launch(S_RESIDUAL, op->b, op->data, op->indices, op->indptr, N, op->Ni, rhs, x, r, partials, 1.0,
+                           -1, skip, st, &grid);
+        if (rc) return rc;
+    } else {
+        Sel sel{0, 0, N, 1, 0, N};
+        DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB);
+                       k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
+                           op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
+        DGB_LAUNCH_OK();
+    }
     k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
     DGB_LAUNCH_OK();
     return 0;
-}
-
-int dgb_bsr_residual(const double *data, const int32_t *indices, const int32_t *indptr,
-                     int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
-                     double *partials, double *sumsq, void *stream) {
-    return dgb_bsr_residual_skip(data, indices, indptr, n_brow, b, rhs, x, r, partials, sumsq,
-                                 nullptr, stream);
 }
 
 int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream) {
@@ -423,62 +449,77 @@ int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_
     return 0;
 }
 
-// one relaxation launch over a selection
-static int relax_launch(const double *data, const int32_t *indices, const int32_t *indptr,
-                        const double *dinv, int32_t b, const double *rhs, const double *x_in,
-                        double *x_out, double omega, Sel sel, const int32_t *skip, cudaStream_t st) {
+// one generic relaxation launch over a selection
+static int relax_launch(const dgb_operator *op, const double *rhs, const double *x_in, double *x_out,
+                        double omega, Sel sel, const int32_t *skip, cudaStream_t st) {
     if (sel.count <= 0) return 0;
-    DGB_DISPATCH_B(b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
-                          data, indices, indptr, dinv, rhs, x_in, x_out, nullptr, omega, sel, skip));
+    DGB_DISPATCH_B(op->b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+                              op->data, op->indices, op->indptr, op->dinv, rhs, x_in, x_out, nullptr, omega, sel, skip));
     DGB_LAUNCH_OK();
     return 0;
 }
 
-static int wavefront_pass(const double *data, const int32_t *indices, const int32_t *indptr,
-                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
-                          double *x, double omega, int direction, const int32_t *skip,
-                          cudaStream_t st) {
+static int wavefront_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
+                          const int32_t *skip, cudaStream_t st) {
+    const int Ni = op->Ni, Nj = op->Nj;
     const int ndiag = Ni + Nj - 1;
     for (int k = 0; k < ndiag; ++k) {
         const int c = direction > 0 ? k : ndiag - 1 - k;
         const int i_lo = c - (Nj - 1) > 0 ? c - (Nj - 1) : 0;
         const int i_hi = c < Ni - 1 ? c : Ni - 1;
         Sel sel{2, c, Ni, Nj, i_lo, i_hi - i_lo + 1};
-        int rc = relax_launch(data, indices, indptr, dinv, b, rhs, x, x, omega, sel, skip, st);
+        int rc = relax_launch(op, rhs, x, x, omega, sel, skip, st);
         if (rc) return rc;
     }
     return 0;
 }
 
-int dgb_block_gs_pass(const double *data, const int32_t *indices, const int32_t *indptr,
-                      const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
-                      double *x, int32_t direction, int32_t mode, const int32_t *skip,
-                      void *stream) {
-    DGB_ARG(data && indices && indptr && dinv && rhs && x && Ni > 0 && Nj > 0);
+// exact lexicographic order, either kernel family
+static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
+                              const int32_t *skip, cudaStream_t st) {
+    if (use_stream(op) && op->gs_data != nullptr)
+        return gs_rows_launch(op->b, op->gs_data, rhs, x, op->Ni, op->Nj, op->stencil, direction, omega, skip, st);
+    return wavefront_pass(op, rhs, x, omega, direction, skip, st);
+}
+
+int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int32_t direction,
+                      int32_t mode, const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && rhs && x);
     DGB_ARG(direction == 1 || direction == -1);
     cudaStream_t st = (cudaStream_t)stream;
+    const int N = op->Ni * op->Nj;
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
-            Sel sel{1, colour, Ni, Nj, 0, Ni * Nj};
-            int rc = relax_launch(data, indices, indptr, dinv, b, rhs, x, x, 1.0, sel, skip, st);
+            if (use_stream(op) && op->gs_data != nullptr) {
+                rc = stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x, x, nullptr,
+                                   1.0, colour, skip, st, nullptr);
+            } else {
+                Sel sel{1, colour, op->Ni, op->Nj, 0, N};
+                rc = relax_launch(op, rhs, x, x, 1.0, sel, skip, st);
+            }
             if (rc) return rc;
         }
         return 0;
     }
-    return wavefront_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, x, 1.0, direction, skip, st);
+    return lexicographic_pass(op, rhs, x, 1.0, direction, skip, st);
 }
 
-int dgb_block_relax_sweep(const double *data, const int32_t *indices, const int32_t *indptr,
-                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b,
-                          const double *rhs, const double *x_in, double *x_out, double omega,
-                          void *stream) {
-    DGB_ARG(data && indices && indptr && dinv && rhs && x_in && x_out && Ni > 0 && Nj > 0);
+int dgb_block_relax_sweep(const dgb_operator *op, const double *rhs, const double *x_in,
+                          double *x_out, double omega, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && rhs && x_in && x_out);
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_in == x_out)
-        return wavefront_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, x_out, omega, +1, nullptr, st);
-    Sel sel{0, 0, Ni, Nj, 0, Ni * Nj};
-    return relax_launch(data, indices, indptr, dinv, b, rhs, x_in, x_out, omega, sel, nullptr, st);
+    const int N = op->Ni * op->Nj;
+    if (x_in == x_out) return lexicographic_pass(op, rhs, x_out, omega, +1, nullptr, st);
+    if (use_stream(op) && op->gs_data != nullptr)
+        return stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x_in, x_out,
+                             nullptr, omega, -1, nullptr, st, nullptr);
+    Sel sel{0, 0, op->Ni, op->Nj, 0, N};
+    return relax_launch(op, rhs, x_in, x_out, omega, sel, nullptr, st);
 }
 
 int dgb_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream) {
@@ -494,19 +535,17 @@ int dgb_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, vo
     return 0;
 }
 
-int dgb_block_gauss_seidel_pyamg(const double *data, const int32_t *indices,
-                                 const int32_t *indptr, const double *dinv, int32_t Ni,
-                                 int32_t Nj, int32_t b, const double *rhs, double *u,
+int dgb_block_gauss_seidel_pyamg(const dgb_operator *op, const double *rhs, double *u,
                                  int32_t direction, int32_t max_iterations, int32_t mode,
                                  int32_t check_residual, dgb_smoother_ctl *ctl, double *partials,
                                  double *sumsq, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
     DGB_ARG(ctl && partials && sumsq);
     DGB_ARG(direction == 0 || direction == 1 || direction == -1);
-    const int32_t N = Ni * Nj;
-    const int64_t n = (int64_t)N * b;
-    int rc;
+    const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
     if (check_residual) {
-        rc = dgb_bsr_residual(data, indices, indptr, N, b, rhs, u, nullptr, partials, sumsq, stream);
+        rc = dgb_bsr_residual(op, rhs, u, nullptr, partials, sumsq, nullptr, stream);
         if (rc) return rc;
         rc = dgb_smoother_begin(ctl, sumsq, n, stream);
         if (rc) return rc;
@@ -514,16 +553,15 @@ int dgb_block_gauss_seidel_pyamg(const double *data, const int32_t *indices,
     const int32_t *skip = check_residual ? &ctl->skip : nullptr;
     for (int it = 0; it < max_iterations; ++it) {
         if (direction >= 0) {
-            rc = dgb_block_gs_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, u, +1, mode, skip, stream);
+            rc = dgb_block_gs_pass(op, rhs, u, +1, mode, skip, stream);
             if (rc) return rc;
         }
         if (direction <= 0) {
-            rc = dgb_block_gs_pass(data, indices, indptr, dinv, Ni, Nj, b, rhs, u, -1, mode, skip, stream);
+            rc = dgb_block_gs_pass(op, rhs, u, -1, mode, skip, stream);
             if (rc) return rc;
         }
         if (check_residual) {
-            rc = dgb_bsr_residual_skip(data, indices, indptr, N, b, rhs, u, nullptr, partials, sumsq,
-                                       skip, stream);
+            rc = dgb_bsr_residual(op, rhs, u, nullptr, partials, sumsq, skip, stream);
             if (rc) return rc;
             rc = dgb_smoother_check(ctl, sumsq, n, stream);
             if (rc) return rc;

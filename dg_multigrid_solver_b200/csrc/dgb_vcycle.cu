@@ -7,29 +7,22 @@
 //   k==1: coarse grid solver 'smoother' = the pre-smoother with max_iterations = 10
 #include "dgb_common.cuh"
 
-extern "C" int dgb_bsr_residual_skip(const double *, const int32_t *, const int32_t *, int32_t,
-                                     int32_t, const double *, const double *, double *, double *,
-                                     double *, const int32_t *, void *);
-
 namespace dgb {
 
 static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, dgb_smoother_ctl *ctl,
                   double *partials, double *sumsq, void *stream) {
     if (iterations <= 0) return 0;
-    const size_t nbytes = sizeof(double) * (size_t)L.Ni * L.Nj * L.b;
+    const size_t nbytes = sizeof(double) * (size_t)L.op.Ni * L.op.Nj * L.op.b;
     switch (L.smoother) {
     case DGB_SMOOTHER_BLOCK_GS_PYAMG:
-        return dgb_block_gauss_seidel_pyamg(L.data, L.indices, L.indptr, L.dinv, L.Ni, L.Nj, L.b, L.rhs,
-                                            L.u, L.direction, iterations, o.gs_mode, o.check_residual,
-                                            ctl, partials, sumsq, stream);
+        return dgb_block_gauss_seidel_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode,
+                                            o.check_residual, ctl, partials, sumsq, stream);
     case DGB_SMOOTHER_BLOCK_JACOBI: {
         // relaxation.py:123-150: iteration 1 is Jacobi into a fresh buffer, then `u = u_new`
         // aliases the two, so the remaining iterations are in-place forward sweeps.
-        int rc = dgb_block_relax_sweep(L.data, L.indices, L.indptr, L.dinv, L.Ni, L.Nj, L.b, L.rhs, L.u,
-                                       L.r, L.omega, stream);
+        int rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.r, L.omega, stream);
         for (int it = 1; it < iterations && rc == 0; ++it)
-            rc = dgb_block_relax_sweep(L.data, L.indices, L.indptr, L.dinv, L.Ni, L.Nj, L.b, L.rhs, L.r,
-                                       L.r, L.omega, stream);
+            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.r, L.r, L.omega, stream);
         if (rc) return rc;
         DGB_CUDA_OK(cudaMemcpyAsync(L.u, L.r, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return 0;
@@ -37,8 +30,7 @@ static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, 
     case DGB_SMOOTHER_BLOCK_GS: {
         int rc = 0;
         for (int it = 0; it < iterations && rc == 0; ++it)   // relaxation.py:170-195 (forward only)
-            rc = dgb_block_relax_sweep(L.data, L.indices, L.indptr, L.dinv, L.Ni, L.Nj, L.b, L.rhs, L.u,
-                                       L.u, L.omega, stream);
+            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.u, L.omega, stream);
         return rc;
     }
     default:
@@ -57,13 +49,11 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     const dgb_level &C = lv[k - 1];
     if ((rc = smooth(L, o, L.pre_iterations, ctl + k, partials, sumsq, stream))) return rc;
     // residual = RHS - BSR @ u (solver.py:150)
-    if ((rc = dgb_bsr_residual_skip(L.data, L.indices, L.indptr, L.Ni * L.Nj, L.b, L.rhs, L.u, L.r,
-                                    partials, sumsq, nullptr, stream)))
-        return rc;
-    if ((rc = dgb_restrict(C.transfer_kind, C.R, C.nc, C.nf, C.Ni, C.Nj, L.r, C.rhs, stream))) return rc;
-    DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.Ni * C.Nj * C.b, st));   // solver.py:171
+    if ((rc = dgb_bsr_residual(&L.op, L.rhs, L.u, L.r, partials, sumsq, nullptr, stream))) return rc;
+    if ((rc = dgb_restrict(C.transfer_kind, C.R, C.nc, C.nf, C.op.Ni, C.op.Nj, L.r, C.rhs, stream))) return rc;
+    DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.op.Ni * C.op.Nj * C.op.b, st));   // solver.py:171
     if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream))) return rc;
-    if ((rc = dgb_prolong_add(C.transfer_kind, C.P, C.nc, C.nf, C.Ni, C.Nj, C.u, L.u, stream))) return rc;
+    if ((rc = dgb_prolong_add(C.transfer_kind, C.P, C.nc, C.nf, C.op.Ni, C.op.Nj, C.u, L.u, stream))) return rc;
     return smooth(L, o, L.post_iterations, ctl + k, partials, sumsq, stream);
 }
 
@@ -74,14 +64,14 @@ extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_
     DGB_ARG(h_levels && h_opts && ctl && partials && sumsq && nlevels >= 1);
     for (int k = 0; k < nlevels; ++k) {
         const dgb_level &L = h_levels[k];
-        DGB_ARG(L.data && L.indices && L.indptr && L.dinv && L.rhs && L.u && L.r);
+        DGB_ARG(L.op.data && L.op.indices && L.op.indptr && L.op.dinv && L.rhs && L.u && L.r);
         if (k < nlevels - 1) {
             DGB_ARG(L.R && L.P && (L.transfer_kind == DGB_TRANSFER_P || L.transfer_kind == DGB_TRANSFER_H));
             const dgb_level &F = h_levels[k + 1];
             if (L.transfer_kind == DGB_TRANSFER_P) {
-                DGB_ARG(L.nc == L.b && L.nf == F.b && L.Ni == F.Ni && L.Nj == F.Nj);
+                DGB_ARG(L.nc == L.op.b && L.nf == F.op.b && L.op.Ni == F.op.Ni && L.op.Nj == F.op.Nj);
             } else {
-                DGB_ARG(L.nc == L.b && L.nf == 4 * F.b && 2 * L.Ni == F.Ni && 2 * L.Nj == F.Nj);
+                DGB_ARG(L.nc == L.op.b && L.nf == 4 * F.op.b && 2 * L.op.Ni == F.op.Ni && 2 * L.op.Nj == F.op.Nj);
             }
         }
     }

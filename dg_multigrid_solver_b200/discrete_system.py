@@ -61,9 +61,8 @@ class Poisson:
         b = grid.N_DOF_sol["u"]
         N = grid.Ni * grid.Nj
         nnzb = int(L.dgb_poisson_nnzb(grid.Ni, grid.Nj, flags))
-        # +2 doubles of slack: the streaming kernels issue 16-byte aligned bulk copies
-        grid._data_store = torch.empty(nnzb * b * b + 2, dtype=torch.float64, device="cuda")
-        grid.d_data = grid._data_store[:nnzb * b * b].view(nnzb, b, b)
+        from .grid import padded_blocks
+        grid.d_data = padded_blocks(nnzb, b)
         grid.d_indices = torch.empty(nnzb, dtype=torch.int32, device="cuda")
         grid.d_indptr = torch.empty(N + 1, dtype=torch.int32, device="cuda")
         grid.d_minv = torch.empty((N, b, b), dtype=torch.float64, device="cuda")
@@ -74,6 +73,7 @@ class Poisson:
         grid.flags = flags
         grid.nnzb = nnzb
         grid._BSR = None
+        grid.stencil = flags & (_lib.FLAG_PERIODIC_I | _lib.FLAG_PERIODIC_J)   # structure is ours by construction
         prepare_smoother_data(grid)
 
     def assemble_RHS_Poisson(self, grid):
@@ -94,16 +94,28 @@ class Poisson:
 
 
 def prepare_smoother_data(grid):
-    """Inverse diagonal blocks, once per level (the reference recomputes them on every smoother
-    call: pyamg_relaxation.py:230-231)."""
+    """Inverse diagonal blocks and the smoother stream, once per level (the reference recomputes
+    the block inverses on every smoother call: pyamg_relaxation.py:230-231)."""
     torch = _lib.require_cuda()
+    from .grid import padded_blocks
     b = grid.d_data.shape[1]
     N = grid.d_indptr.numel() - 1
+    st = _lib.stream_ptr()
     grid.d_dinv = torch.empty((N, b, b), dtype=torch.float64, device="cuda")
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.call("dgb_block_diag_inverse", grid.d_data, grid.d_indices, grid.d_indptr, N, b, grid.d_dinv, info,
-              _lib.stream_ptr())
+    _lib.call("dgb_block_diag_inverse", grid.d_data, grid.d_indices, grid.d_indptr, N, b, grid.d_dinv, info, st)
     grid._dinv_info = info
+    if grid.stencil >= 0:
+        # belt and braces: the streaming kernels rely on the closed-form 5-point structure
+        mism = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.call("dgb_check_stencil", grid.d_indices, grid.d_indptr, grid.Ni, grid.Nj, grid.stencil, mism, st)
+        if int(mism.item()) != 0:
+            grid.stencil = -1
+    if grid.stencil >= 0:
+        grid.d_gs = padded_blocks(int(grid.d_indices.numel()), b)
+        _lib.call("dgb_build_gs_stream", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_dinv, N, b, grid.d_gs, st)
+    else:
+        grid.d_gs = None
     return grid.d_dinv
 
 

@@ -89,6 +89,16 @@ class Geometry:
         return self._dev
 
 
+def padded_blocks(nblocks, b):
+    """[nblocks, b, b] fp64 device tensor with 16 bytes of readable slack behind it (the streaming
+    kernels issue 16-byte aligned bulk copies that may over-read by up to 8 bytes)."""
+    torch = _lib.require_cuda()
+    store = torch.zeros(nblocks * b * b + 2, dtype=torch.float64, device="cuda")
+    view = store[:nblocks * b * b].view(nblocks, b, b)
+    view._dgb_store = store
+    return view
+
+
 class _ElementView:
     """What callers of the reference read from grid.elements[i, j]."""
 
@@ -139,6 +149,7 @@ class Grid:
         self.d_data = self.d_indices = self.d_indptr = None
         self.d_minv = self.d_dinv = self.d_rhs = self.d_gs = None
         self._BSR = self._RHS = self._area_host = None
+        self.stencil = -1          # >= 0 once the BSR structure is verified to be the 5-point DG stencil
         self.BSR_E = self.BSR_D = self.BSR_F = None
         self.Epsilon = None
 
@@ -163,10 +174,23 @@ class Grid:
         self._BSR = value
         if value is not None:
             torch = _lib.require_cuda()
-            self.d_data = torch.from_numpy(np.ascontiguousarray(value.data, dtype=np.float64)).cuda()
+            data = np.ascontiguousarray(value.data, dtype=np.float64)
+            self.d_data = padded_blocks(data.shape[0], data.shape[1])
+            self.d_data.copy_(torch.from_numpy(data))
             self.d_indices = torch.from_numpy(np.ascontiguousarray(value.indices, dtype=np.int32)).cuda()
             self.d_indptr = torch.from_numpy(np.ascontiguousarray(value.indptr, dtype=np.int32)).cuda()
             self.d_dinv = self.d_gs = None
+            self.stencil = -1
+
+    def operator(self):
+        """dgb_operator view of this level's device arrays (include/dgb200.h)."""
+        b = int(self.d_data.shape[1])
+        return _lib.Operator(Ni=int(self.Ni), Nj=int(self.Nj), b=b, nnzb=int(self.d_indices.numel()),
+                             stencil=int(self.stencil), reserved=0,
+                             data=self.d_data.data_ptr(), indices=self.d_indices.data_ptr(),
+                             indptr=self.d_indptr.data_ptr(),
+                             dinv=self.d_dinv.data_ptr() if self.d_dinv is not None else None,
+                             gs_data=self.d_gs.data_ptr() if self.d_gs is not None else None)
 
     @property
     def RHS(self):

@@ -81,10 +81,9 @@ class Relaxation:
             mode = _lib.GS_REDBLACK if gs_mode in ("redblack", _lib.GS_REDBLACK) else _lib.GS_LEXICOGRAPHIC
         if check_residual is not None:
             chk = 1 if check_residual else 0
-        b = grid.d_data.shape[1]
-        _lib.call("dgb_block_gauss_seidel_pyamg", grid.d_data, grid.d_indices, grid.d_indptr, _ensure_dinv(grid),
-                  grid.Ni, grid.Nj, b, d_rhs, d_u, _DIRECTION[direction], int(max_iterations), mode, chk,
-                  ws.ctl, ws.partials, ws.sumsq, _lib.stream_ptr())
+        _ensure_dinv(grid)
+        _lib.call("dgb_block_gauss_seidel_pyamg", grid.operator(), d_rhs, d_u, _DIRECTION[direction],
+                  int(max_iterations), mode, chk, ws.ctl, ws.partials, ws.sumsq, _lib.stream_ptr())
         if host:
             check_dinv(grid)
             if chk:
@@ -105,9 +104,9 @@ class Relaxation:
         block-GS pass; reproduced as such."""
         torch = _lib.require_cuda()
         d_rhs, d_u, host = cls._prep(grid, RHS, u)
-        b = grid.d_data.shape[1]
         st = _lib.stream_ptr()
-        args = (grid.d_data, grid.d_indices, grid.d_indptr, _ensure_dinv(grid), grid.Ni, grid.Nj, b, d_rhs)
+        _ensure_dinv(grid)
+        args = (grid.operator(), d_rhs)
         if int(max_iterations) > 0:
             d_new = torch.empty_like(d_u)
             _lib.call("dgb_block_relax_sweep", *args, d_u, d_new, float(omega), st)
@@ -123,11 +122,11 @@ class Relaxation:
     def block_gauss_seidel(cls, grid, RHS, u=None, direction="forward", omega=1, max_iterations=1e3):
         """dgfem/relaxation.py:170-195 (forward lexicographic order; `direction` is ignored there)."""
         d_rhs, d_u, host = cls._prep(grid, RHS, u)
-        b = grid.d_data.shape[1]
         st = _lib.stream_ptr()
+        _ensure_dinv(grid)
+        op = grid.operator()
         for _ in range(int(max_iterations)):
-            _lib.call("dgb_block_relax_sweep", grid.d_data, grid.d_indices, grid.d_indptr, _ensure_dinv(grid),
-                      grid.Ni, grid.Nj, b, d_rhs, d_u, d_u, float(omega), st)
+            _lib.call("dgb_block_relax_sweep", op, d_rhs, d_u, d_u, float(omega), st)
         if host:
             check_dinv(grid)
             return d_u.cpu().numpy()
@@ -147,8 +146,7 @@ def bsr_apply(grid, x):
     torch = _lib.require_cuda()
     d_x, host = _to_device(x)
     y = torch.empty_like(d_x)
-    _lib.call("dgb_bsr_apply", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_indptr.numel() - 1,
-              grid.d_data.shape[1], d_x, y, _lib.stream_ptr())
+    _lib.call("dgb_bsr_apply", grid.operator(), d_x, y, _lib.stream_ptr())
     return y.cpu().numpy() if host else y
 
 
@@ -157,6 +155,5 @@ def residual_norm(grid, rhs, x, want_residual=False):
     torch = _lib.require_cuda()
     ws = _Workspace.get()
     r = torch.empty_like(rhs) if want_residual else None
-    _lib.call("dgb_bsr_residual", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_indptr.numel() - 1,
-              grid.d_data.shape[1], rhs, x, r, ws.partials, ws.sumsq, _lib.stream_ptr())
+    _lib.call("dgb_bsr_residual", grid.operator(), rhs, x, r, ws.partials, ws.sumsq, None, _lib.stream_ptr())
     return ws.sumsq, r

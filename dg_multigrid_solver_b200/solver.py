@@ -85,9 +85,7 @@ class Solver:
             r = torch.zeros(N * b, dtype=torch.float64, device="cuda")
             vecs.append((rhs, u, r))
             L = levels[k]
-            L.Ni, L.Nj, L.b, L.nnzb = g.Ni, g.Nj, b, int(g.d_indices.numel())
-            L.data, L.indices, L.indptr, L.dinv = (g.d_data.data_ptr(), g.d_indices.data_ptr(),
-                                                   g.d_indptr.data_ptr(), g.d_dinv.data_ptr())
+            L.op = g.operator()
             L.rhs, L.u, L.r = rhs.data_ptr(), u.data_ptr(), r.data_ptr()
             # smoother settings come from the coarsening that links this level to the next coarser
             # one; the coarsest level uses the first link's (dgfem/solver.py:143,202)
@@ -191,14 +189,14 @@ class Solver:
         host = self._load(rhs_k, RHS)
         self._load(u_k, u)
         fine_rhs = fine.d_rhs
+        fine_op = fine.operator()
         b = fine.d_data.shape[1]
         nrow = fine.d_indptr.numel() - 1
         n_dof = float(nrow * b)
         st = _lib.stream_ptr()
 
         def rms():
-            _lib.call("dgb_bsr_residual", fine.d_data, fine.d_indices, fine.d_indptr, nrow, b, fine_rhs, u_k, None,
-                      H["partials"], H["sumsq"], st)
+            _lib.call("dgb_bsr_residual", fine_op, fine_rhs, u_k, None, H["partials"], H["sumsq"], None, st)
             return float(np.sqrt(H["sumsq"].item() / n_dof))
         n = 0
         residual_0 = rms()

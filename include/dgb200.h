@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DGB_ABI_VERSION 1
+#define DGB_ABI_VERSION 2
 
 /* ---- status ------------------------------------------------------------------------- */
 int dgb_abi_version(void);
@@ -57,23 +57,48 @@ typedef struct dgb_smoother_ctl {
     int32_t calls;    /* smoother calls since the block was zeroed */
 } dgb_smoother_ctl;
 
+/* ---- the operator of one level ---------------------------------------------------------
+ * HOST struct of DEVICE pointers, passed by pointer to the solve-phase entry points.
+ * `stencil` selects the kernel family:
+ *   -1  arbitrary BSR matrix (Ni*Nj block rows): generic row-per-thread kernels;
+ *   >=0 the DG 5-point block stencil on the Ni x Nj element grid, value = DGB_FLAG_PERIODIC_I|J
+ *       bits, structure verified once with dgb_check_stencil: the TMA-streaming kernels are
+ *       used.  They need 16 bytes of readable slack behind data / gs_data (bulk copies are
+ *       16-byte aligned) and gs_data for the smoothers (else the generic kernels run). */
+typedef struct dgb_operator {
+    int32_t Ni, Nj;          /* element grid; N = Ni*Nj block rows                        */
+    int32_t b, nnzb;         /* block size, number of stored blocks                        */
+    int32_t stencil;         /* see above                                                  */
+    int32_t reserved;
+    const double *data;      /* [nnzb][b][b]                  (dgfem/discrete_system.py:145) */
+    const int32_t *indices;  /* [nnzb]                                                     */
+    const int32_t *indptr;   /* [N+1]                                                      */
+    const double *dinv;      /* [N][b][b] inverse diagonal blocks (NULL for apply/residual) */
+    const double *gs_data;   /* [nnzb][b][b] smoother stream, or NULL                      */
+} dgb_operator;
+
+#define DGB_FLAG_PERIODIC_I 1
+#define DGB_FLAG_PERIODIC_J 2
+#define DGB_FLAG_MINV 4
+
+/* 0 = auto (streaming kernels where the operator allows), 1 = generic kernels only.
+ * Returns the previous setting. */
+int dgb_set_kernel_path(int32_t path);
+/* Error flag of the asynchronous kernels (0 ok, 1 = TMA/mbarrier wait timed out, 2 = row
+ * dependency wait timed out).  Synchronises the device. */
+int dgb_device_error(int32_t reset);
+
 /* ---- K5: block-sparse operator apply / residual ---------------------------------------
  * replaces  grid.BSR @ u  (scipy bsr_matvec) -- dgfem/solver.py:117,119,150;
  *           dgfem/relaxation.py:202,208; utils/helpers.py:39 */
-int dgb_bsr_apply(const double *data, const int32_t *indices, const int32_t *indptr,
-                  int32_t n_brow, int32_t b, const double *x, double *y, void *stream);
+int dgb_bsr_apply(const dgb_operator *h_op, const double *x, double *y, void *stream);
 
 /* r = rhs - A x (r may be NULL: norm only) and sum(r^2) into *sumsq (device scalar),
  * replaces  RHS - grid.BSR @ u  + compute_Lp_norm(.,2)  (utils/helpers.py:16-39).
- * `partials` is a workspace of dgb_partials_len() doubles. */
-int dgb_bsr_residual(const double *data, const int32_t *indices, const int32_t *indptr,
-                     int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
-                     double *partials, double *sumsq, void *stream);
-
-/* Same, gated by an optional device flag (dgb_smoother_ctl.skip): a no-op when *skip != 0. */
-int dgb_bsr_residual_skip(const double *data, const int32_t *indices, const int32_t *indptr,
-                          int32_t n_brow, int32_t b, const double *rhs, const double *x, double *r,
-                          double *partials, double *sumsq, const int32_t *skip, void *stream);
+ * `partials` is a workspace of dgb_partials_len() doubles.  skip: optional device flag
+ * (dgb_smoother_ctl.skip); the call is a no-op when *skip != 0. */
+int dgb_bsr_residual(const dgb_operator *h_op, const double *rhs, const double *x, double *r,
+                     double *partials, double *sumsq, const int32_t *skip, void *stream);
 
 /* sum(v^2) of a plain vector into *sumsq (device scalar). */
 int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream);
@@ -92,31 +117,32 @@ int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_
                         const double *dinv, int32_t n_brow, int32_t b, double *gs_data,
                         void *stream);
 
+/* *mismatch (device int) = number of block rows whose (indptr, indices) differ from the
+ * closed-form 5-point stencil of an Ni x Nj DG grid with the given periodicity flags. */
+int dgb_check_stencil(const int32_t *indices, const int32_t *indptr, int32_t Ni, int32_t Nj,
+                      int32_t flags, int32_t *mismatch, void *stream);
+
 /* ---- K7: block Gauss-Seidel, one directional pass ---------------------------------------
  * replaces  pyamg.amg_core.block_gauss_seidel(Ap,Aj,Ax,x,b,Dinv,row_start,row_stop,row_step,bs)
  *           (dgfem/pyamg_relaxation.py:252-255).
  * direction: +1 forward (rows 0..N-1), -1 backward (rows N-1..0).
- * mode: DGB_GS_LEXICOGRAPHIC reproduces the lexicographic order exactly through the
- *       anti-diagonal wavefront c=i+j of the Ni x Nj element grid (requires the 5-point
+ * mode: DGB_GS_LEXICOGRAPHIC reproduces the lexicographic order exactly (row-pipelined kernel,
+ *       or the anti-diagonal wavefront c=i+j with the generic kernels; both need the 5-point
  *       block stencil the DG operator has); DGB_GS_REDBLACK is the 2-colour multicolour
  *       variant (forward = colour 0 then 1, backward = 1 then 0).
  * skip: optional device flag (ctl->skip); when non-zero the pass is a no-op. */
 #define DGB_GS_LEXICOGRAPHIC 0
 #define DGB_GS_REDBLACK 1
-int dgb_block_gs_pass(const double *data, const int32_t *indices, const int32_t *indptr,
-                      const double *dinv, int32_t Ni, int32_t Nj, int32_t b, const double *rhs,
-                      double *x, int32_t direction, int32_t mode, const int32_t *skip,
-                      void *stream);
+int dgb_block_gs_pass(const dgb_operator *h_op, const double *rhs, double *x, int32_t direction,
+                      int32_t mode, const int32_t *skip, void *stream);
 
 /* ---- K8: one block-row relaxation sweep, x_out_i = omega*Dinv_i(rhs_i - sum_{j!=i} A_ij x_in_j)
  *                                                   + (1-omega) x_in_i
  * x_out != x_in : block-Jacobi            (first iteration of dgfem/relaxation.py:123-150)
- * x_out == x_in : forward block-GS, lexicographic wavefront (dgfem/relaxation.py:170-195 and
+ * x_out == x_in : forward block-GS, lexicographic order (dgfem/relaxation.py:170-195 and
  *                 iterations >= 2 of block_jacobi, whose `u = u_new` aliases the buffers). */
-int dgb_block_relax_sweep(const double *data, const int32_t *indices, const int32_t *indptr,
-                          const double *dinv, int32_t Ni, int32_t Nj, int32_t b,
-                          const double *rhs, const double *x_in, double *x_out, double omega,
-                          void *stream);
+int dgb_block_relax_sweep(const dgb_operator *h_op, const double *rhs, const double *x_in,
+                          double *x_out, double omega, void *stream);
 
 /* ---- smoother control ------------------------------------------------------------------ */
 /* ctl->res0 = sqrt(*sumsq / n); skip = diverged = iters = 0; calls += 1 */
@@ -129,9 +155,7 @@ int dgb_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, vo
  *           (dgfem/relaxation.py:198-218); u is updated IN PLACE (the host wrapper copies).
  * direction: 0 symmetric, +1 forward, -1 backward.  `check_residual` = 0 drops the
  * per-iteration residual norms (and with them the early exit) -- NOT reference semantics. */
-int dgb_block_gauss_seidel_pyamg(const double *data, const int32_t *indices,
-                                 const int32_t *indptr, const double *dinv, int32_t Ni,
-                                 int32_t Nj, int32_t b, const double *rhs, double *u,
+int dgb_block_gauss_seidel_pyamg(const dgb_operator *h_op, const double *rhs, double *u,
                                  int32_t direction, int32_t max_iterations, int32_t mode,
                                  int32_t check_residual, dgb_smoother_ctl *ctl, double *partials,
                                  double *sumsq, void *stream);
@@ -156,17 +180,14 @@ int dgb_prolong_add(int32_t kind, const double *P, int32_t nc, int32_t nf, int32
  * levels[0] is the coarsest grid, levels[nlevels-1] the finest (the order of
  * Solver.grids); levels[k].R/P map between level k (coarse) and k+1 (fine). */
 typedef struct dgb_level {
-    int32_t Ni, Nj, b, nnzb;
-    const double *data;      /* [nnzb][b][b]                                   */
-    const int32_t *indices;  /* [nnzb]                                         */
-    const int32_t *indptr;   /* [Ni*Nj+1]                                      */
-    const double *dinv;      /* [Ni*Nj][b][b]                                  */
+    dgb_operator op;
     double *rhs;             /* [Ni*Nj*b] work: right-hand side of this level  */
     double *u;               /* [Ni*Nj*b] work: iterate of this level          */
     double *r;               /* [Ni*Nj*b] work: residual                       */
     /* transfer between this level (coarse side) and the next finer one */
     int32_t transfer_kind;   /* 0 on the finest level                          */
     int32_t nc, nf;          /* R is [nc x nf], P is [nf x nc]                 */
+    int32_t pad0;
     const double *R;
     const double *P;
     /* smoother settings of the coarsening that owns this level (paramfile.yml:20-65) */
@@ -237,9 +258,6 @@ int dgb_metrics(const dgb_tables *t, const double *xn, const double *yn, int32_t
  * (dgfem/face.py:115-280).  flags: bit0 periodic in i (O-grid), bit1 periodic in j,
  * bit2 multiply by the inverse mass matrix.
  * Outputs: indptr[N+1], indices[nnzb], data[nnzb][b][b], minv[N][b][b]. */
-#define DGB_FLAG_PERIODIC_I 1
-#define DGB_FLAG_PERIODIC_J 2
-#define DGB_FLAG_MINV 4
 int64_t dgb_poisson_nnzb(int32_t Ni, int32_t Nj, int32_t flags);
 int dgb_assemble_poisson(const dgb_tables *t, const double *vol, const double *face,
                          const double *area, int32_t Ni, int32_t Nj, double nu, double sigma,

@@ -1,0 +1,92 @@
+#!/usr/bin/env python3
+"""Time the solve-phase kernels of one level in isolation (CUDA events), both kernel paths.
+usage: probe_kernels.py NI NJ P [reps]   -- Rectangle NI x NJ elements, solution degree P."""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "oracle")]
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from dg_multigrid_solver_b200 import _lib  # noqa: E402
+from dg_multigrid_solver_b200.discrete_system import DiscreteSystem  # noqa: E402
+from dg_multigrid_solver_b200.grid import Geometry, Grid  # noqa: E402
+from dg_multigrid_solver_b200.settings import Settings  # noqa: E402
+
+
+def nodes(ni, nj, P):
+    from dg_multigrid_solver_b200.tables import gauss_lobatto_nodes
+    xi = gauss_lobatto_nodes(P + 1)
+
+    def line(n):
+        e = np.linspace(-1.0, 1.0, n + 1)
+        out = np.empty(n * P + 1)
+        for k in range(n):
+            out[k * P:(k + 1) * P + 1] = e[k] + (e[k + 1] - e[k]) * (xi + 1.0) / 2.0
+        return out
+    lx, ly = line(ni), line(nj)
+    return np.repeat(lx[None, :], ly.size, axis=0), np.repeat(ly[:, None], lx.size, axis=1)
+
+
+def main():
+    ni, nj, p = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+    only = sys.argv[5] if len(sys.argv) > 5 else ""
+    Pg = max(p, 1)
+    prm = bench.make_params(max(ni, nj), Pg, "lexicographic", True)
+    prm["solution"]["u"]["polynomial degree"] = p
+    s = Settings(prm)
+    s.update_setting("solver.method", "smoother")
+    s.update_setting("solver.discretization", "dg")
+    geo = Geometry(None, s, nodes=nodes(ni, nj, Pg))
+    g = Grid(geo, ["u"]).initialize({"u": p}, None)
+    DiscreteSystem(s).problem.assemble(g)
+    g.release_geometry()
+    L = _lib.load()
+    st = _lib.stream_ptr()
+    op = g.operator()
+    N, b, nnzb = g.Ni * g.Nj, g.b, int(g.d_indices.numel())
+    ab = bench.algorithmic_bytes(nnzb, N, b)
+    x = torch.randn(N * b, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    part = torch.zeros(L.dgb_partials_len(), dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        c.record(); torch.cuda.synchronize()
+        return a.elapsed_time(c) / reps
+    out = {"Ni": ni, "Nj": nj, "p": p, "b": b, "GB": {k: v / 1e9 for k, v in ab.items()}}
+    calls = {
+        "apply": (lambda: _lib.call("dgb_bsr_apply", op, x, y, st), ab["apply"]),
+        "residual": (lambda: _lib.call("dgb_bsr_residual", op, g.d_rhs, x, None, part, ss, None, st), ab["residual"]),
+        "gs_fwd": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, 1, 0, None, st), ab["gs_pass"]),
+        "gs_bwd": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, -1, 0, None, st), ab["gs_pass"]),
+        "redblack": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, 1, 1, None, st), ab["gs_pass"]),
+        "jacobi": (lambda: _lib.call("dgb_block_relax_sweep", op, g.d_rhs, x, y, 1.0, st), ab["gs_pass"]),
+    }
+    for path, nm in ((0, "stream"), (1, "generic")):
+        if only and nm != only.split(":")[0]:
+            continue
+        L.dgb_set_kernel_path(path)
+        for k, (fn, nbytes) in calls.items():
+            if only and ":" in only and k != only.split(":")[1]:
+                continue
+            if path == 1 and k.startswith("gs_") and max(ni, nj) > 600:
+                continue
+            ms = timed(fn)
+            out[f"{nm}.{k}"] = {"ms": round(ms, 4), "GB/s": round(nbytes / ms / 1e6, 1)}
+    L.dgb_set_kernel_path(0)
+    out["device_error"] = L.dgb_device_error(1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
