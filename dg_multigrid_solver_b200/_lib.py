@@ -29,7 +29,8 @@ class Operator(ctypes.Structure):
     """dgb_operator (include/dgb200.h): host struct of device pointers."""
     _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
                 ("stencil", c_i32), ("reserved", c_i32),
-                ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp), ("gs_data", c_vp)]
+                ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp), ("gs_data", c_vp),
+                ("gs_mailbox", c_vp)]
 
 
 class Level(ctypes.Structure):

@@ -343,8 +343,8 @@ bool stream_supported(int b);
 int stream_launch(int mode, int b, const double *data, const int32_t *indices, const int32_t *indptr, int N,
                   int Ni, const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
                   int colour, const int32_t *skip, cudaStream_t st, int *grid_out);
-int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, int Ni, int Nj, int flags, int dir,
-                   double omega, const int32_t *skip, cudaStream_t st);
+int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double *mbox, int Ni, int Nj, int flags,
+                   int dir, double omega, const int32_t *skip, cudaStream_t st);
 enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
 
 static bool use_stream(const dgb_operator *op) {
@@ -477,8 +477,9 @@ static int wavefront_pass(const dgb_operator *op, const double *rhs, double *x, 
 // exact lexicographic order, either kernel family
 static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
                               const int32_t *skip, cudaStream_t st) {
-    if (use_stream(op) && op->gs_data != nullptr)
-        return gs_rows_launch(op->b, op->gs_data, rhs, x, op->Ni, op->Nj, op->stencil, direction, omega, skip, st);
+    if (use_stream(op) && op->gs_data != nullptr && op->gs_mailbox != nullptr)
+        return gs_rows_launch(op->b, op->gs_data, rhs, x, op->gs_mailbox, op->Ni, op->Nj, op->stencil, direction,
+                              omega, skip, st);
     return wavefront_pass(op, rhs, x, omega, direction, skip, st);
 }
 

@@ -244,7 +244,16 @@ k_stream(const double *__restrict__ data, const int32_t *__restrict__ indices,
 }
 
 // =========================================================================================
-// k_gs_rows
+// k_gs_rows  (v2: no fences)
+//
+// Row j may process element i once row j-1 (in sweep order) has finished element i.  The value
+// it needs from that row, x(i, j-1), is handed over
+//   - through a shared-memory ring + progress counter when both rows live in the same CTA,
+//   - through a global "mailbox" otherwise: the producer stores the 8-byte values themselves
+//     (ld/st.cg, L2), the consumer spins until none of them is the sentinel (all-ones NaN) and
+//     writes the sentinel back.  Data doubles as its own flag, so no release/acquire fence
+//     (MEMBAR / CCTL.IVALL) sits on the critical path.  The mailbox is an [N*b] vector owned by
+//     the level, all-sentinel outside a pass.
 // =========================================================================================
 template <int B>
 struct GsCfg {
@@ -252,14 +261,16 @@ struct GsCfg {
     static constexpr int P = (B == 9) ? 3 : (B == 4) ? 4 : 1;       // lanes per scalar row
     static constexpr int CW = (B + P - 1) / P;                      // columns per lane
     static constexpr int RS = (B + 31) / 32;                        // row slots per lane (P == 1)
-    static constexpr int W = B <= 9 ? 8 : B <= 16 ? 4 : B <= 25 ? 2 : 1;   // rows (warps) per CTA
-    static constexpr int S = B <= 9 ? 4 : 3;                        // ring stages per warp
+    static constexpr int W = B <= 9 ? 16 : B <= 16 ? 4 : B <= 25 ? 2 : 1;   // rows (warps) per CTA
+    static constexpr int S = 3;                                     // TMA ring stages per warp
+    static constexpr int RING = 8;                                  // x hand-over ring slots per warp
     static constexpr int STAGE_D = (5 * B2 + 2 + 1) & ~1;           // doubles per stage, even
     static constexpr int BP = (B + 1) & ~1;
     static constexpr int PD = 16 / gcd_c(B, 16);
-    static constexpr int WARP_D = S * STAGE_D + 7 * BP;             // stages | vs[5] | xprev | rs
+    static constexpr int WARP_D = S * STAGE_D + 7 * BP + RING * BP; // stages | vs[5] | xprev | rs | ring
     static constexpr size_t oBar = sizeof(double) * W * WARP_D;
-    static constexpr size_t SMEM = oBar + sizeof(uint64_t) * W * S;
+    static constexpr size_t oProg = oBar + sizeof(uint64_t) * W * S;
+    static constexpr size_t SMEM = oProg + sizeof(int) * W;
 };
 
 struct GsElem {
@@ -276,40 +287,45 @@ __device__ __forceinline__ GsElem gs_elem(const Stencil &S_, int i, int j) {
     E.e = c[0];
     E.n = 0;
 #pragma unroll
-    for (int s = 0; s < 5; ++s) E.col[s] = -1;
+    for (int t = 0; t < 5; ++t) {       // sorted position t holds the slot whose rank is t
+        int v = -1;
 #pragma unroll
-    for (int s = 0; s < 5; ++s)
-        if (rk[s] >= 0) {
-            E.col[rk[s]] = c[s];
-            ++E.n;
-        }
+        for (int s = 0; s < 5; ++s) v = (rk[s] == t) ? c[s] : v;
+        E.col[t] = v;
+        E.n += (v >= 0);
+    }
     E.tdiag = rk[0];
     E.shift = (int)((S_.row_start(i, j) * GsCfg<B>::B2) & 1);
     return E;
 }
 
-// work[0] = ticket counter, work[1 + sr] = completed elements of sweep row sr
+__device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1LL; }
+
+// work[0] = ticket counter
 template <int B>
 __global__ void __launch_bounds__(GsCfg<B>::W * 32)
-k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double *x, Stencil S_, int dir,
-          double omega, int *work, int *err, const int32_t *__restrict__ skip) {
+k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double *x, double *mbox, Stencil S_,
+          int dir, double omega, int *work, int *err, const int32_t *__restrict__ skip) {
     using C = GsCfg<B>;
-    constexpr int B2 = C::B2, S = C::S, P = C::P, CW = C::CW, RS = C::RS, BP = C::BP;
+    constexpr int B2 = C::B2, S = C::S, P = C::P, CW = C::CW, RS = C::RS, BP = C::BP, RING = C::RING, W = C::W;
     if (skip != nullptr && *skip != 0) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_ticket;
+    volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::oProg);
     if (threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
+    if (threadIdx.x < W) s_prog[threadIdx.x] = 0;
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ni = S_.Ni, Nj = S_.Nj;
-    const int sr = s_ticket * C::W + w;        // row index in sweep order
+    const int sr = s_ticket * W + w;           // row index in sweep order
     if (sr >= Nj) return;
     const int j = dir > 0 ? sr : Nj - 1 - sr;
-    int *prog = work + 1;
     double *wbase = reinterpret_cast<double *>(smem) + (size_t)w * C::WARP_D;
     double *vs = wbase + S * C::STAGE_D;       // [5][BP]
     double *xprev = vs + 5 * BP;
     double *rsv = xprev + BP;
+    double *ring = rsv + BP;                   // [RING][BP], written by this warp, read by warp w+1
+    const double *ring_pred = ring - C::WARP_D;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::oBar) + w * S;
     if (lane == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -336,11 +352,16 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     const int part = P > 1 ? lane % P : 0;
     const int c0 = part * CW, c1 = min(B, c0 + CW);
     const int q = (lane & 15) / C::PD;
-    const bool has_pred = sr > 0;
-    int seen = 0;                               // cached progress of the predecessor row
+    // hand-over topology
+    const int pred = sr == 0 ? 0 : (w > 0 ? 1 : 2);                       // 0 none, 1 smem ring, 2 global mailbox
+    const int succ = sr == Nj - 1 ? 0 : (w < W - 1 ? 1 : 2);
+    const int pred_off = -dir * Ni;                                        // element offset to the predecessor row
+    const double sentinel = __longlong_as_double(-1LL);
 
-    double V[5][RS], rhsv[RS], xold[RS];
+    double V[5][RS], rhsv[RS], xold[RS], PV[RS];
+    // neighbour vectors that do not come from the predecessor row (old values, or this row's own)
     auto load_vectors = [&](const GsElem &E, int e_prev, double (&Vv)[5][RS], double (&rh)[RS], double (&xo)[RS]) {
+        const int e_pred = pred ? E.e + pred_off : -2;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             const int col = E.col[t];
@@ -348,7 +369,8 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             for (int sl = 0; sl < RS; ++sl) {
                 const int c = lane + 32 * sl;
                 Vv[t][sl] = 0.0;
-                if (t < E.n && col != E.e && col != e_prev && c < B) Vv[t][sl] = __ldcg(x + (size_t)col * B + c);
+                if (t < E.n && col != E.e && col != e_prev && col != e_pred && c < B)
+                    Vv[t][sl] = __ldcg(x + (size_t)col * B + c);
             }
         }
 #pragma unroll
@@ -359,33 +381,69 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             xo[sl] = (own && omega != 1.0) ? __ldcg(x + (size_t)E.e * B + r) : 0.0;
         }
     };
-    auto dep_poll = [&]() {
-        int v = 0;
-        if (lane == 0) v = ld_acquire(prog + (sr - 1));
-        seen = __shfl_sync(0xffffffffu, v, 0);
+    // predecessor-row value for sweep index idx: raw fetch (may hold sentinels for the mailbox)
+    auto pred_fetch_global = [&](int e_pred, double (&pv)[RS]) {
+#pragma unroll
+        for (int sl = 0; sl < RS; ++sl) {
+            const int c = lane + 32 * sl;
+            pv[sl] = (c < B) ? __ldcg(mbox + (size_t)e_pred * B + c) : 0.0;
+        }
+    };
+    auto pred_ready_global = [&](int e_pred, double (&pv)[RS]) -> bool {
+        bool mine = true;
+#pragma unroll
+        for (int sl = 0; sl < RS; ++sl) {
+            const int c = lane + 32 * sl;
+            if (c < B && is_sentinel(pv[sl])) mine = false;
+        }
+        const bool ok = __all_sync(0xffffffffu, mine);
+        if (ok) {
+#pragma unroll
+            for (int sl = 0; sl < RS; ++sl) {
+                const int c = lane + 32 * sl;
+                if (c < B) __stcg(mbox + (size_t)e_pred * B + c, sentinel);      // hand the slot back
+            }
+        }
+        return ok;
+    };
+    auto pred_read_ring = [&](int idx, double (&pv)[RS]) {
+#pragma unroll
+        for (int sl = 0; sl < RS; ++sl) {
+            const int c = lane + 32 * sl;
+            pv[sl] = (c < B) ? ring_pred[(idx % RING) * BP + c] : 0.0;
+        }
     };
 
     GsElem cur = gs_elem<B>(S_, dir > 0 ? 0 : Ni - 1, j);
     int e_prev = -1;
-    bool pre = false;
+    bool have_pv = false;
+    load_vectors(cur, e_prev, V, rhsv, xold);
     for (int idx = 0; idx < Ni; ++idx) {
-        if (!pre) {
-            if (has_pred) {
-                int spin = 0;
-                while (seen < idx + 1) {
-                    dep_poll();
-                    if (++spin > kSpinLimit || ((spin & 255) == 255 && *(volatile int *)err != 0)) {
+        // ---- predecessor-row value (blocking only if the prefetch below did not get it) ----
+        if (pred != 0 && !have_pv) {
+            int spin = 0;
+            if (pred == 1) {
+                while (s_prog[w - 1] < idx + 1) {
+                    if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return; }
+                }
+                __threadfence_block();
+                pred_read_ring(idx, PV);
+            } else {
+                for (;;) {
+                    pred_fetch_global(cur.e + pred_off, PV);
+                    if (pred_ready_global(cur.e + pred_off, PV)) break;
+                    if (++spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
                         if (lane == 0) atomicExch(err, 2);
                         return;
                     }
                 }
             }
-            load_vectors(cur, e_prev, V, rhsv, xold);
         }
         const int s = idx % S;
         if (!mbar_wait(&full[s], (idx / S) & 1, err)) return;
         const double *st = wbase + (size_t)s * C::STAGE_D + cur.shift;
-        // publish the prefetched neighbour vectors to this warp's scratch
+        // ---- publish the neighbour vectors to this warp's scratch ----
+        const int e_pred = pred ? cur.e + pred_off : -2;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             const int col = cur.col[t];
@@ -393,24 +451,30 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
 #pragma unroll
                 for (int sl = 0; sl < RS; ++sl) {
                     const int c = lane + 32 * sl;
-                    if (c < B) vs[t * BP + c] = V[t][sl];
+                    if (c < B) vs[t * BP + c] = (col == e_pred) ? PV[sl] : V[t][sl];
                 }
             }
         }
         __syncwarp();
-        // prefetch the next element's vectors if its dependency is already satisfied
+        // ---- prefetch for the next element ----
         GsElem nxt = cur;
-        double Vn[5][RS], rhsn[RS], xoldn[RS];
-        pre = false;
+        double Vn[5][RS], rhsn[RS], xoldn[RS], PVn[RS];
+        bool have_next = false, polled = false;
         if (idx + 1 < Ni) {
             nxt = gs_elem<B>(S_, dir > 0 ? idx + 1 : Ni - 2 - idx, j);
-            if (has_pred && seen < idx + 2) dep_poll();
-            if (!has_pred || seen >= idx + 2) {
-                load_vectors(nxt, cur.e, Vn, rhsn, xoldn);
-                pre = true;
+            load_vectors(nxt, cur.e, Vn, rhsn, xoldn);
+            if (pred == 1) {
+                if (s_prog[w - 1] >= idx + 2) {
+                    __threadfence_block();
+                    pred_read_ring(idx + 1, PVn);
+                    have_next = true;
+                }
+            } else if (pred == 2) {
+                pred_fetch_global(nxt.e + pred_off, PVn);      // evaluated after the arithmetic below
+                polled = true;
             }
         }
-        // phase A: acc_r = sum over off-diagonal blocks of A[t][r][:] . x_col(t)
+        // ---- phase A: acc_r = sum over off-diagonal blocks of A[t][r][:] . x_col(t) ----
         double acc[RS];
 #pragma unroll
         for (int sl = 0; sl < RS; ++sl) acc[sl] = 0.0;
@@ -442,7 +506,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             if (own) rsv[r] = rhsv[sl] - acc[sl];
         }
         __syncwarp();
-        // phase B: x_i = Dinv_i * rsum
+        // ---- phase B: x_i = Dinv_i * rsum ----
         const double *D = st + cur.tdiag * B2;
         double xn[RS];
 #pragma unroll
@@ -460,6 +524,13 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                 if (r < B) xn[sl] = skew_dot<B>(D + r * B, rsv, q);
             }
         }
+        // ---- hand the result over: x, own scratch, successor row ----
+        if (succ == 1) {     // ring slot must have been consumed: warp w+1 finished element idx - RING
+            int spin = 0;
+            while (s_prog[w + 1] < idx - RING + 1) {
+                if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return; }
+            }
+        }
 #pragma unroll
         for (int sl = 0; sl < RS; ++sl) {
             const int r = P > 1 ? r0 : lane + 32 * sl;
@@ -468,29 +539,33 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                 const double v = (omega == 1.0) ? xn[sl] : omega * xn[sl] + (1.0 - omega) * xold[sl];
                 __stcg(x + (size_t)cur.e * B + r, v);
                 xprev[r] = v;
+                if (succ == 1) ring[(idx % RING) * BP + r] = v;
+                if (succ == 2) __stcg(mbox + (size_t)cur.e * B + r, v);
             }
         }
         __syncwarp();
         if (lane == 0) {
-            __threadfence();
-            st_release(prog + sr, idx + 1);
+            __threadfence_block();
+            s_prog[w] = idx + 1;
             if (idx + S < Ni) {
                 fence_proxy_async();
                 issue(idx + S);
             }
         }
+        if (polled) have_next = pred_ready_global(nxt.e + pred_off, PVn);
+        // ---- rotate ----
         e_prev = cur.e;
         cur = nxt;
-        if (pre) {
+        have_pv = have_next;
 #pragma unroll
-            for (int t = 0; t < 5; ++t)
+        for (int t = 0; t < 5; ++t)
 #pragma unroll
-                for (int sl = 0; sl < RS; ++sl) V[t][sl] = Vn[t][sl];
+            for (int sl = 0; sl < RS; ++sl) V[t][sl] = Vn[t][sl];
 #pragma unroll
-            for (int sl = 0; sl < RS; ++sl) {
-                rhsv[sl] = rhsn[sl];
-                xold[sl] = xoldn[sl];
-            }
+        for (int sl = 0; sl < RS; ++sl) {
+            rhsv[sl] = rhsn[sl];
+            xold[sl] = xoldn[sl];
+            PV[sl] = PVn[sl];
         }
     }
 }
@@ -581,27 +656,27 @@ int stream_launch(int mode, int b, const double *data, const int32_t *indices, c
 }
 
 template <int B>
-static int gs_rows_launch_t(const double *gs, const double *rhs, double *x, Stencil S_, int dir, double omega,
-                            const int32_t *skip, cudaStream_t st) {
+static int gs_rows_launch_t(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
+                            double omega, const int32_t *skip, cudaStream_t st) {
     using C = GsCfg<B>;
     static bool configured = false;
     if (!configured) {
         DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_rows<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
-    DGB_CUDA_OK(cudaMemsetAsync(g_work, 0, sizeof(int) * (S_.Nj + 1), st));
+    DGB_CUDA_OK(cudaMemsetAsync(g_work, 0, sizeof(int), st));
     const int grid = (S_.Nj + C::W - 1) / C::W;
-    k_gs_rows<B><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, S_, dir, omega, g_work, g_err, skip);
+    k_gs_rows<B><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, g_work, g_err, skip);
     DGB_LAUNCH_OK();
     return 0;
 }
 
-int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, int Ni, int Nj, int flags, int dir,
-                   double omega, const int32_t *skip, cudaStream_t st) {
-    int rc = ensure_work(Nj);
+int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double *mbox, int Ni, int Nj, int flags,
+                   int dir, double omega, const int32_t *skip, cudaStream_t st) {
+    int rc = ensure_work(0);
     if (rc) return rc;
     Stencil S_{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
-    DGB_DISPATCH_B(b, return (gs_rows_launch_t<B>(gs, rhs, x, S_, dir, omega, skip, st)));
+    DGB_DISPATCH_B(b, return (gs_rows_launch_t<B>(gs, rhs, x, mbox, S_, dir, omega, skip, st)));
     return 0;
 }
 

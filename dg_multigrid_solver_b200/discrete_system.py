@@ -114,8 +114,10 @@ def prepare_smoother_data(grid):
     if grid.stencil >= 0:
         grid.d_gs = padded_blocks(int(grid.d_indices.numel()), b)
         _lib.call("dgb_build_gs_stream", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_dinv, N, b, grid.d_gs, st)
+        # row hand-over mailbox of the lexicographic GS kernel: all-ones (sentinel NaN) outside a pass
+        grid.d_mailbox = torch.full((N * b,), -1, dtype=torch.int64, device="cuda").view(torch.float64)
     else:
-        grid.d_gs = None
+        grid.d_gs = grid.d_mailbox = None
     return grid.d_dinv
 
 

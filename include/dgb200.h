@@ -75,6 +75,8 @@ typedef struct dgb_operator {
     const int32_t *indptr;   /* [N+1]                                                      */
     const double *dinv;      /* [N][b][b] inverse diagonal blocks (NULL for apply/residual) */
     const double *gs_data;   /* [nnzb][b][b] smoother stream, or NULL                      */
+    double *gs_mailbox;      /* [N*b] row hand-over scratch of the lexicographic GS kernel:
+                                every 8 bytes 0xFF (all-ones NaN) outside a pass, or NULL   */
 } dgb_operator;
 
 #define DGB_FLAG_PERIODIC_I 1
