@@ -244,7 +244,7 @@ k_stream(const double *__restrict__ data, const int32_t *__restrict__ indices,
 }
 
 // =========================================================================================
-// k_gs_rows  (v2: no fences)
+// k_gs_rows
 //
 // Row j may process element i once row j-1 (in sweep order) has finished element i.  The value
 // it needs from that row, x(i, j-1), is handed over
@@ -254,27 +254,38 @@ k_stream(const double *__restrict__ data, const int32_t *__restrict__ indices,
 //     writes the sentinel back.  Data doubles as its own flag, so no release/acquire fence
 //     (MEMBAR / CCTL.IVALL) sits on the critical path.  The mailbox is an [N*b] vector owned by
 //     the level, all-sentinel outside a pass.
+// Everything else a row reads is a sequential stream along the row and is prefetched deep:
+//   - its block row (GS stream) through a TMA bulk-copy ring (S stages, mbarrier complete_tx),
+//   - rhs(e), the old x of the next element of the row and of the next row through a cp.async
+//     ring D elements ahead (HBM latency under load is ~2 us, an element takes ~0.3 us).
 // =========================================================================================
 template <int B>
+struct GsDefault {
+    static constexpr int W = B <= 9 ? 16 : B <= 16 ? 4 : B <= 25 ? 2 : 1;   // rows (warps) per CTA
+    static constexpr int S = 3;                                             // TMA ring stages per warp
+};
+template <int B, int W_ = GsDefault<B>::W, int S_ = GsDefault<B>::S>
 struct GsCfg {
     static constexpr int B2 = B * B;
     static constexpr int P = (B == 9) ? 3 : (B == 4) ? 4 : 1;       // lanes per scalar row
     static constexpr int CW = (B + P - 1) / P;                      // columns per lane
     static constexpr int RS = (B + 31) / 32;                        // row slots per lane (P == 1)
-    static constexpr int W = B <= 9 ? 16 : B <= 16 ? 4 : B <= 25 ? 2 : 1;   // rows (warps) per CTA
-    static constexpr int S = 3;                                     // TMA ring stages per warp
+    static constexpr int W = W_;                                    // rows (warps) per CTA
+    static constexpr int S = S_;                                    // TMA ring stages per warp
+    static constexpr int D = B <= 9 ? 8 : 4;                        // cp.async prefetch distance (elements)
     static constexpr int RING = 8;                                  // x hand-over ring slots per warp
     static constexpr int STAGE_D = (5 * B2 + 2 + 1) & ~1;           // doubles per stage, even
     static constexpr int BP = (B + 1) & ~1;
     static constexpr int PD = 16 / gcd_c(B, 16);
-    static constexpr int WARP_D = S * STAGE_D + 7 * BP + RING * BP; // stages | vs[5] | xprev | rs | ring
-    static constexpr size_t oBar = sizeof(double) * W * WARP_D;
-    static constexpr size_t oProg = oBar + sizeof(uint64_t) * W * S;
+    // per warp: stages | vs[5] | xprev | rs | pvs | ring[RING] | vring[D+1][3]
+    static constexpr int WARP_D = S * STAGE_D + 8 * BP + RING * BP + (D + 1) * 3 * BP;
+    static constexpr size_t oBar = sizeof(double) * W * WARP_D;          // full[W][S], hand[W][RING]
+    static constexpr size_t oProg = oBar + sizeof(uint64_t) * W * (S + RING);
     static constexpr size_t SMEM = oProg + sizeof(int) * W;
 };
 
 struct GsElem {
-    int e, n, tdiag, shift;
+    int e, n, tdiag;
     int col[5];
 };
 
@@ -295,25 +306,41 @@ __device__ __forceinline__ GsElem gs_elem(const Stencil &S_, int i, int j) {
         E.n += (v >= 0);
     }
     E.tdiag = rk[0];
-    E.shift = (int)((S_.row_start(i, j) * GsCfg<B>::B2) & 1);
     return E;
 }
 
 __device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1LL; }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // work[0] = ticket counter
-template <int B>
-__global__ void __launch_bounds__(GsCfg<B>::W * 32)
+template <int B, int WW = GsDefault<B>::W, int SS = GsDefault<B>::S>
+__global__ void __launch_bounds__(WW * 32)
 k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double *x, double *mbox, Stencil S_,
           int dir, double omega, int *work, int *err, const int32_t *__restrict__ skip) {
-    using C = GsCfg<B>;
+    using C = GsCfg<B, WW, SS>;
     constexpr int B2 = C::B2, S = C::S, P = C::P, CW = C::CW, RS = C::RS, BP = C::BP, RING = C::RING, W = C::W;
+    constexpr int D = C::D;
     if (skip != nullptr && *skip != 0) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_ticket;
     volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::oProg);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::oBar);
     if (threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
     if (threadIdx.x < W) s_prog[threadIdx.x] = 0;
+    // one thread per warp initialises that warp's barriers (before any warp may touch a neighbour's)
+    if ((threadIdx.x & 31) == 0) {
+        uint64_t *bw = bars + (threadIdx.x >> 5) * (S + RING);
+        for (int s = 0; s < S + RING; ++s) mbar_init(&bw[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ni = S_.Ni, Nj = S_.Nj;
@@ -321,24 +348,47 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     if (sr >= Nj) return;
     const int j = dir > 0 ? sr : Nj - 1 - sr;
     double *wbase = reinterpret_cast<double *>(smem) + (size_t)w * C::WARP_D;
-    double *vs = wbase + S * C::STAGE_D;       // [5][BP]
-    double *xprev = vs + 5 * BP;
-    double *rsv = xprev + BP;
-    double *ring = rsv + BP;                   // [RING][BP], written by this warp, read by warp w+1
+    double *vs = wbase + S * C::STAGE_D;       // [5][BP]  directly loaded neighbour vectors (wrap cases)
+    double *xprev = vs + 5 * BP;               // previous element of this row (new value)
+    double *rsv = xprev + BP;                  // rhs - sum offdiag
+    double *pvs = rsv + BP;                    // predecessor-row value when it came through the mailbox
+    double *ring = pvs + BP;                   // [RING][BP], written by this warp, read by warp w+1
+    double *vring = ring + RING * BP;          // [D+1][3][BP]: rhs | x side | x next row
     const double *ring_pred = ring - C::WARP_D;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::oBar) + w * S;
-    if (lane == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-        fence_barrier_init();
-        fence_proxy_async();
+    uint64_t *full = bars + w * (S + RING);    // TMA stage barriers of this warp
+    uint64_t *hand = full + S;                 // hand[slot]: this warp has written ring slot `slot`
+    uint64_t *hand_pred = hand - (S + RING);
+
+    // ---- row constants: block counts and the interior column pattern ----
+    const int n_first = S_.count(0, j), n_last = S_.count(Ni - 1, j), n_int = Ni > 2 ? S_.count(1, j) : 0;
+    const long long k_row = S_.row_start(0, j);
+    auto k0_of = [&](int i) -> long long { return k_row + (i > 0 ? n_first + (long long)(i - 1) * n_int : 0); };
+    auto cnt_of = [&](int i) -> int { return i == 0 ? n_first : (i == Ni - 1 ? n_last : n_int); };
+    GsElem tmpl;                               // columns of an interior element, relative to e
+    tmpl.e = 0; tmpl.n = 0; tmpl.tdiag = 0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) tmpl.col[t] = -1;
+    if (Ni > 2) {
+        tmpl = gs_elem<B>(S_, 1, j);
+#pragma unroll
+        for (int t = 0; t < 5; ++t) tmpl.col[t] = tmpl.col[t] >= 0 ? tmpl.col[t] - tmpl.e : (1 << 30);
     }
-    __syncwarp();
+    auto elem_at = [&](int i) -> GsElem {
+        if (i > 0 && i < Ni - 1) {
+            GsElem E;
+            E.e = j * Ni + i;
+            E.n = tmpl.n;
+            E.tdiag = tmpl.tdiag;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) E.col[t] = t < tmpl.n ? E.e + tmpl.col[t] : -1;
+            return E;
+        }
+        return gs_elem<B>(S_, i, j);
+    };
     const char *gbytes = reinterpret_cast<const char *>(gs);
     auto issue = [&](int idx) {     // lane 0: bulk copy of element idx's block row into its stage
         const int i = dir > 0 ? idx : Ni - 1 - idx;
-        const long long k0 = S_.row_start(i, j);
-        const int cnt = S_.count(i, j);
-        const size_t byte0 = (size_t)k0 * B2 * 8, byte1 = byte0 + (size_t)cnt * B2 * 8;
+        const size_t byte0 = (size_t)k0_of(i) * B2 * 8, byte1 = byte0 + (size_t)cnt_of(i) * B2 * 8;
         const size_t a0 = byte0 & ~(size_t)15, a1 = (byte1 + 15) & ~(size_t)15;
         const int s = idx % S;
         mbar_expect_tx(&full[s], (uint32_t)(a1 - a0));
@@ -346,6 +396,28 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     };
     if (lane == 0)
         for (int idx = 0; idx < S && idx < Ni; ++idx) issue(idx);
+    const int jn = j + dir;                                  // next row in sweep order (old values)
+    const bool next_row_ok = jn >= 0 && jn < Nj;
+    // cp.async prefetch of the sequential vector streams for sweep index n (one commit per call)
+    auto prefetch_vectors = [&](int n) {
+        if (n < Ni) {
+            const int i = dir > 0 ? n : Ni - 1 - n;
+            const int e = j * Ni + i;
+            double *slot = vring + (size_t)(n % (D + 1)) * 3 * BP;
+            const int iside = i + dir;
+#pragma unroll
+            for (int sl = 0; sl < RS; ++sl) {
+                const int c = lane + 32 * sl;
+                if (c < B) {
+                    cp_async8(slot + c, rhs + (size_t)e * B + c);
+                    if (iside >= 0 && iside < Ni) cp_async8(slot + BP + c, x + (size_t)(e + dir) * B + c);
+                    if (next_row_ok) cp_async8(slot + 2 * BP + c, x + (size_t)(e + dir * Ni) * B + c);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    for (int n = 0; n < D; ++n) prefetch_vectors(n);
 
     // lane -> (scalar row, column range)
     const int r0 = P > 1 ? lane / P : lane;
@@ -358,30 +430,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     const int pred_off = -dir * Ni;                                        // element offset to the predecessor row
     const double sentinel = __longlong_as_double(-1LL);
 
-    double V[5][RS], rhsv[RS], xold[RS], PV[RS];
-    // neighbour vectors that do not come from the predecessor row (old values, or this row's own)
-    auto load_vectors = [&](const GsElem &E, int e_prev, double (&Vv)[5][RS], double (&rh)[RS], double (&xo)[RS]) {
-        const int e_pred = pred ? E.e + pred_off : -2;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            const int col = E.col[t];
-#pragma unroll
-            for (int sl = 0; sl < RS; ++sl) {
-                const int c = lane + 32 * sl;
-                Vv[t][sl] = 0.0;
-                if (t < E.n && col != E.e && col != e_prev && col != e_pred && c < B)
-                    Vv[t][sl] = __ldcg(x + (size_t)col * B + c);
-            }
-        }
-#pragma unroll
-        for (int sl = 0; sl < RS; ++sl) {
-            const int r = P > 1 ? r0 : lane + 32 * sl;
-            const bool own = (P > 1) ? (part == 0 && r < B) : (r < B);
-            rh[sl] = own ? rhs[(size_t)E.e * B + r] : 0.0;
-            xo[sl] = (own && omega != 1.0) ? __ldcg(x + (size_t)E.e * B + r) : 0.0;
-        }
-    };
-    // predecessor-row value for sweep index idx: raw fetch (may hold sentinels for the mailbox)
+    double PV[RS];
     auto pred_fetch_global = [&](int e_pred, double (&pv)[RS]) {
 #pragma unroll
         for (int sl = 0; sl < RS; ++sl) {
@@ -406,96 +455,177 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         }
         return ok;
     };
-    auto pred_read_ring = [&](int idx, double (&pv)[RS]) {
+
+    // ---- interior pattern of this row: which sorted block position holds which neighbour ----
+    int tP = -1, tV = -1, tS = -1, tN = -1, tD = 0;
+    bool fast_ok = Ni > 2;
+    if (Ni > 2) {
+        tD = tmpl.tdiag;
 #pragma unroll
-        for (int sl = 0; sl < RS; ++sl) {
-            const int c = lane + 32 * sl;
-            pv[sl] = (c < B) ? ring_pred[(idx % RING) * BP + c] : 0.0;
+        for (int t = 0; t < 5; ++t) {
+            if (t < tmpl.n && t != tD) {
+                const int off = tmpl.col[t];
+                if (off == -dir) tV = t;                                   // previous element (new value)
+                else if (pred != 0 && off == pred_off) tP = t;             // predecessor row (new value)
+                else if (off == dir) tS = t;                               // next element of the row (old)
+                else if (next_row_ok && off == dir * Ni) tN = t;           // next row (old)
+                else fast_ok = false;                                      // periodic wrap: generic path
+            }
         }
+    }
+    const uint32_t full_a = smem_u32(full), hand_a = smem_u32(hand), handp_a = smem_u32(hand_pred);
+    const uint32_t stage_a = smem_u32(wbase);
+    auto wait_a = [&](uint32_t bar, uint32_t parity) -> bool {
+        for (int spin = 0; spin < kSpinLimit; ++spin) {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (ok) return true;
+            if ((spin & 1023) == 1023 && *(volatile int *)err != 0) return false;
+        }
+        atomicExch(err, 1);
+        return false;
+    };
+    // running TMA source offset of the element to be issued next (sweep index idx + S)
+    auto issue_a = [&](int idx) {
+        const int i = dir > 0 ? idx : Ni - 1 - idx;
+        const size_t byte0 = (size_t)k0_of(i) * B2 * 8, byte1 = byte0 + (size_t)cnt_of(i) * B2 * 8;
+        const size_t a0 = byte0 & ~(size_t)15, a1 = (byte1 + 15) & ~(size_t)15;
+        const uint32_t bar = full_a + 8u * (uint32_t)(idx % S);
+        const uint32_t dst = stage_a + (uint32_t)((idx % S) * C::STAGE_D * 8);
+        const uint32_t bytes = (uint32_t)(a1 - a0);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(gbytes + a0), "r"(bytes), "r"(bar)
+                     : "memory");
     };
 
-    GsElem cur = gs_elem<B>(S_, dir > 0 ? 0 : Ni - 1, j);
+    GsElem cur = elem_at(dir > 0 ? 0 : Ni - 1);
     int e_prev = -1;
     bool have_pv = false;
-    load_vectors(cur, e_prev, V, rhsv, xold);
-    for (int idx = 0; idx < Ni; ++idx) {
-        // ---- predecessor-row value (blocking only if the prefetch below did not get it) ----
-        if (pred != 0 && !have_pv) {
+    auto generic_step = [&](int idx) -> bool {
+        const int i = dir > 0 ? idx : Ni - 1 - idx;
+        constexpr bool fast = false;
+        const int e = j * Ni + i;
+        // ---- predecessor-row value ----
+        if (pred == 1) {
+            if (!wait_a(handp_a + 8u * (uint32_t)(idx % RING), (idx / RING) & 1)) return false;
+        } else if (pred == 2 && !have_pv) {
             int spin = 0;
-            if (pred == 1) {
-                while (s_prog[w - 1] < idx + 1) {
-                    if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return; }
+            for (;;) {
+                pred_fetch_global(e + pred_off, PV);
+                if (pred_ready_global(e + pred_off, PV)) break;
+                if (++spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
+                    if (lane == 0) atomicExch(err, 2);
+                    return false;
                 }
-                __threadfence_block();
-                pred_read_ring(idx, PV);
-            } else {
-                for (;;) {
-                    pred_fetch_global(cur.e + pred_off, PV);
-                    if (pred_ready_global(cur.e + pred_off, PV)) break;
-                    if (++spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
-                        if (lane == 0) atomicExch(err, 2);
-                        return;
+            }
+        }
+        // ---- vectors of this element have landed (cp.async groups complete in order) ----
+        cp_async_wait<D - 1>();
+        const double *vslot = vring + (size_t)(idx % (D + 1)) * 3 * BP;
+        if (pred == 2) {
+#pragma unroll
+            for (int sl = 0; sl < RS; ++sl) {
+                const int c = lane + 32 * sl;
+                if (c < B) pvs[c] = PV[sl];
+            }
+        }
+        const double *pvec = pred == 1 ? ring_pred + (idx % RING) * BP : pvs;
+        if (!fast) {
+            // neighbour vectors that are neither streamed nor handed over (periodic wraps): load now
+            const int e_pred = pred ? e + pred_off : -2;
+            const int e_side = (i + dir >= 0 && i + dir < Ni) ? e + dir : -3;
+            const int e_next = next_row_ok ? e + dir * Ni : -4;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const int col = cur.col[t];
+                if (t < cur.n && col != e && col != e_prev && col != e_pred && col != e_side && col != e_next) {
+#pragma unroll
+                    for (int sl = 0; sl < RS; ++sl) {
+                        const int c = lane + 32 * sl;
+                        if (c < B) vs[t * BP + c] = __ldcg(x + (size_t)col * B + c);
                     }
                 }
             }
         }
         const int s = idx % S;
-        if (!mbar_wait(&full[s], (idx / S) & 1, err)) return;
-        const double *st = wbase + (size_t)s * C::STAGE_D + cur.shift;
-        // ---- publish the neighbour vectors to this warp's scratch ----
-        const int e_pred = pred ? cur.e + pred_off : -2;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            const int col = cur.col[t];
-            if (t < cur.n && col != cur.e && col != e_prev) {
-#pragma unroll
-                for (int sl = 0; sl < RS; ++sl) {
-                    const int c = lane + 32 * sl;
-                    if (c < B) vs[t * BP + c] = (col == e_pred) ? PV[sl] : V[t][sl];
-                }
-            }
-        }
+        if (!wait_a(full_a + 8u * (uint32_t)s, (idx / S) & 1)) return false;
+        const double *st = wbase + (size_t)s * C::STAGE_D + (int)((k0_of(i) * B2) & 1);
         __syncwarp();
-        // ---- prefetch for the next element ----
-        GsElem nxt = cur;
-        double Vn[5][RS], rhsn[RS], xoldn[RS], PVn[RS];
-        bool have_next = false, polled = false;
-        if (idx + 1 < Ni) {
-            nxt = gs_elem<B>(S_, dir > 0 ? idx + 1 : Ni - 2 - idx, j);
-            load_vectors(nxt, cur.e, Vn, rhsn, xoldn);
-            if (pred == 1) {
-                if (s_prog[w - 1] >= idx + 2) {
-                    __threadfence_block();
-                    pred_read_ring(idx + 1, PVn);
-                    have_next = true;
-                }
-            } else if (pred == 2) {
-                pred_fetch_global(nxt.e + pred_off, PVn);      // evaluated after the arithmetic below
-                polled = true;
-            }
+        // ---- early, non-blocking poll of the mailbox for the next element ----
+        double PVn[RS];
+        bool polled = false;
+        if (pred == 2 && idx + 1 < Ni) {
+            pred_fetch_global(e + dir + pred_off, PVn);      // evaluated after the arithmetic below
+            polled = true;
         }
         // ---- phase A: acc_r = sum over off-diagonal blocks of A[t][r][:] . x_col(t) ----
-        double acc[RS];
+        double acc[RS], acc2 = 0.0;
 #pragma unroll
         for (int sl = 0; sl < RS; ++sl) acc[sl] = 0.0;
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            if (t >= cur.n || t == cur.tdiag) continue;
-            const double *v = (cur.col[t] == e_prev) ? xprev : vs + t * BP;
-            const double *A = st + t * B2;
+        int tdiag = tD;
+        if (fast) {
             if (P > 1) {
-                if (r0 < B)
-                    for (int c = c0; c < c1; ++c) acc[0] = fma(A[r0 * B + c], v[c], acc[0]);
+                if (r0 < B) {
+                    const double *Ar = st + r0 * B;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    if (tV >= 0)
+                        for (int c = c0; c < c1; ++c) a0 = fma(Ar[tV * B2 + c], xprev[c], a0);
+                    if (tP >= 0)
+                        for (int c = c0; c < c1; ++c) a1 = fma(Ar[tP * B2 + c], pvec[c], a1);
+                    if (tS >= 0)
+                        for (int c = c0; c < c1; ++c) a2 = fma(Ar[tS * B2 + c], vslot[BP + c], a2);
+                    if (tN >= 0)
+                        for (int c = c0; c < c1; ++c) a3 = fma(Ar[tN * B2 + c], vslot[2 * BP + c], a3);
+                    acc[0] = (a1 + a2) + a3;
+                    acc2 = a0;
+                }
             } else {
 #pragma unroll
                 for (int sl = 0; sl < RS; ++sl) {
                     const int r = lane + 32 * sl;
-                    if (r < B) acc[sl] += skew_dot<B>(A + r * B, v, q);
+                    if (r < B) {
+                        const double *Ar = st + r * B;
+                        double a = 0.0;
+                        if (tP >= 0) a += skew_dot<B>(Ar + tP * B2, pvec, q);
+                        if (tS >= 0) a += skew_dot<B>(Ar + tS * B2, vslot + BP, q);
+                        if (tN >= 0) a += skew_dot<B>(Ar + tN * B2, vslot + 2 * BP, q);
+                        if (tV >= 0) a += skew_dot<B>(Ar + tV * B2, xprev, q);
+                        acc[sl] = a;
+                    }
+                }
+            }
+        } else {
+            tdiag = cur.tdiag;
+            const int e_pred = pred ? e + pred_off : -2;
+            const int e_side = (i + dir >= 0 && i + dir < Ni) ? e + dir : -3;
+            const int e_next = next_row_ok ? e + dir * Ni : -4;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                if (t >= cur.n || t == cur.tdiag) continue;
+                const int col = cur.col[t];
+                const double *v = (col == e_prev) ? xprev
+                                : (col == e_pred) ? pvec
+                                : (col == e_side) ? vslot + BP
+                                : (col == e_next) ? vslot + 2 * BP
+                                                  : vs + t * BP;
+                const double *A = st + t * B2;
+                if (P > 1) {
+                    if (r0 < B)
+                        for (int c = c0; c < c1; ++c) acc[0] = fma(A[r0 * B + c], v[c], acc[0]);
+                } else {
+#pragma unroll
+                    for (int sl = 0; sl < RS; ++sl) {
+                        const int r = lane + 32 * sl;
+                        if (r < B) acc[sl] += skew_dot<B>(A + r * B, v, q);
+                    }
                 }
             }
         }
         if (P > 1) {
-            const double mine = acc[0];
+            const double mine = acc[0] + acc2;
+            acc[0] = mine;
 #pragma unroll
             for (int o = 1; o < P; ++o) acc[0] += __shfl_down_sync(0xffffffffu, mine, o);
         }
@@ -503,17 +633,17 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         for (int sl = 0; sl < RS; ++sl) {
             const int r = P > 1 ? r0 : lane + 32 * sl;
             const bool own = (P > 1) ? (part == 0 && r < B) : (r < B);
-            if (own) rsv[r] = rhsv[sl] - acc[sl];
+            if (own) rsv[r] = vslot[r] - acc[sl];
         }
         __syncwarp();
         // ---- phase B: x_i = Dinv_i * rsum ----
-        const double *D = st + cur.tdiag * B2;
+        const double *Dm = st + tdiag * B2;
         double xn[RS];
 #pragma unroll
         for (int sl = 0; sl < RS; ++sl) xn[sl] = 0.0;
         if (P > 1) {
             if (r0 < B)
-                for (int c = c0; c < c1; ++c) xn[0] = fma(D[r0 * B + c], rsv[c], xn[0]);
+                for (int c = c0; c < c1; ++c) xn[0] = fma(Dm[r0 * B + c], rsv[c], xn[0]);
             const double mine = xn[0];
 #pragma unroll
             for (int o = 1; o < P; ++o) xn[0] += __shfl_down_sync(0xffffffffu, mine, o);
@@ -521,14 +651,15 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
 #pragma unroll
             for (int sl = 0; sl < RS; ++sl) {
                 const int r = lane + 32 * sl;
-                if (r < B) xn[sl] = skew_dot<B>(D + r * B, rsv, q);
+                if (r < B) xn[sl] = skew_dot<B>(Dm + r * B, rsv, q);
             }
         }
         // ---- hand the result over: x, own scratch, successor row ----
-        if (succ == 1) {     // ring slot must have been consumed: warp w+1 finished element idx - RING
+        if (succ == 1 && s_prog[w + 1] < idx - RING + 1) {   // ring slot not yet consumed by warp w+1
             int spin = 0;
             while (s_prog[w + 1] < idx - RING + 1) {
-                if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return; }
+                __nanosleep(40);
+                if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return false; }
             }
         }
 #pragma unroll
@@ -536,38 +667,189 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             const int r = P > 1 ? r0 : lane + 32 * sl;
             const bool own = (P > 1) ? (part == 0 && r < B) : (r < B);
             if (own) {
-                const double v = (omega == 1.0) ? xn[sl] : omega * xn[sl] + (1.0 - omega) * xold[sl];
-                __stcg(x + (size_t)cur.e * B + r, v);
+                double v = xn[sl];
+                if (omega != 1.0) v = omega * v + (1.0 - omega) * __ldcg(x + (size_t)e * B + r);
+                __stcg(x + (size_t)e * B + r, v);
                 xprev[r] = v;
                 if (succ == 1) ring[(idx % RING) * BP + r] = v;
-                if (succ == 2) __stcg(mbox + (size_t)cur.e * B + r, v);
+                if (succ == 2) __stcg(mbox + (size_t)e * B + r, v);
             }
         }
         __syncwarp();
         if (lane == 0) {
-            __threadfence_block();
+            if (succ == 1)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hand_a + 8u * (uint32_t)(idx % RING)) : "memory");
             s_prog[w] = idx + 1;
             if (idx + S < Ni) {
                 fence_proxy_async();
-                issue(idx + S);
+                issue_a(idx + S);
             }
         }
-        if (polled) have_next = pred_ready_global(nxt.e + pred_off, PVn);
+        prefetch_vectors(idx + D);       // reuses the ring slot of element idx - 1
+        have_pv = polled ? pred_ready_global(e + dir + pred_off, PVn) : false;
         // ---- rotate ----
-        e_prev = cur.e;
-        cur = nxt;
-        have_pv = have_next;
+        e_prev = e;
+        if (idx + 1 < Ni && !(fast_ok && idx + 1 >= 1 && idx + 1 <= Ni - 2)) cur = elem_at(dir > 0 ? idx + 1 : Ni - 2 - idx);
 #pragma unroll
-        for (int t = 0; t < 5; ++t)
+        for (int sl = 0; sl < RS; ++sl) PV[sl] = PVn[sl];
+            return true;
+    };
+
+    // ---- sweep: first element (generic), interior elements (lean loop), last element (generic) ----
+    int idx = 0;
+    if (!generic_step(0)) return;
+    idx = 1;
+    if (fast_ok) {
+        // loop-carried counters instead of idx % / idx / arithmetic
+        int s = 1 % S, ph = (1 / S) & 1;                   // TMA stage and its parity
+        int rg = 1 % RING, rph = (1 / RING) & 1;           // hand-over ring slot and parity
+        int vi = 1 % (D + 1);                              // vector ring slot
+        int e = j * Ni + (dir > 0 ? 1 : Ni - 2);
+        int shift = (int)((k0_of(dir > 0 ? 1 : Ni - 2) * B2) & 1);
+        const int flip = (n_int & B2) & 1;
+        const int oV = tV * B2, oP = tP * B2, oS = tS * B2, oN = tN * B2, oD = tD * B2;
+        const int rowoff = (P > 1 ? r0 : 0) * B;
+        const bool rowok = P > 1 ? (r0 < B) : true;
+        const bool own1 = P > 1 && part == 0 && r0 < B;
+        for (; idx <= Ni - 2; ++idx) {
+            // predecessor-row value
+            if (pred == 1) {
+                if (!wait_a(handp_a + 8u * (uint32_t)rg, (uint32_t)rph)) return;
+            } else if (pred == 2 && !have_pv) {
+                int spin = 0;
+                for (;;) {
+                    pred_fetch_global(e + pred_off, PV);
+                    if (pred_ready_global(e + pred_off, PV)) break;
+                    if (++spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
+                        if (lane == 0) atomicExch(err, 2);
+                        return;
+                    }
+                }
+            }
+            cp_async_wait<D - 1>();
+            const double *vslot = vring + vi * (3 * BP);
+            if (pred == 2) {
 #pragma unroll
-            for (int sl = 0; sl < RS; ++sl) V[t][sl] = Vn[t][sl];
+                for (int sl = 0; sl < RS; ++sl) {
+                    const int c = lane + 32 * sl;
+                    if (c < B) pvs[c] = PV[sl];
+                }
+            }
+            const double *pvec = pred == 1 ? ring_pred + rg * BP : pvs;
+            if (!wait_a(full_a + 8u * (uint32_t)s, (uint32_t)ph)) return;
+            const double *st = wbase + s * C::STAGE_D + shift;
+            __syncwarp();
+            double PVn[RS];
+            if (pred == 2) pred_fetch_global(e + dir + pred_off, PVn);     // idx + 1 <= Ni - 1 always exists
+            // phase A
+            double acc[RS];
+            if (P > 1) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                if (rowok) {
+                    const double *Ar = st + rowoff;
+                    if (tV >= 0) {
 #pragma unroll
-        for (int sl = 0; sl < RS; ++sl) {
-            rhsv[sl] = rhsn[sl];
-            xold[sl] = xoldn[sl];
-            PV[sl] = PVn[sl];
+                        for (int c = 0; c < CW; ++c) if (c0 + c < B) a0 = fma(Ar[oV + c0 + c], xprev[c0 + c], a0);
+                    }
+                    if (tP >= 0) {
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) if (c0 + c < B) a1 = fma(Ar[oP + c0 + c], pvec[c0 + c], a1);
+                    }
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) if (c0 + c < B) a2 = fma(Ar[oS + c0 + c], vslot[BP + c0 + c], a2);
+                    if (tN >= 0) {
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) if (c0 + c < B) a3 = fma(Ar[oN + c0 + c], vslot[2 * BP + c0 + c], a3);
+                    }
+                }
+                const double mine = (a1 + a2) + (a3 + a0);
+                acc[0] = mine;
+#pragma unroll
+                for (int o = 1; o < P; ++o) acc[0] += __shfl_down_sync(0xffffffffu, mine, o);
+                if (own1) rsv[r0] = vslot[r0] - acc[0];
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < RS; ++sl) {
+                    const int r = lane + 32 * sl;
+                    if (r < B) {
+                        const double *Ar = st + r * B;
+                        double a = skew_dot<B>(Ar + oS, vslot + BP, q);
+                        if (tP >= 0) a += skew_dot<B>(Ar + oP, pvec, q);
+                        if (tN >= 0) a += skew_dot<B>(Ar + oN, vslot + 2 * BP, q);
+                        if (tV >= 0) a += skew_dot<B>(Ar + oV, xprev, q);
+                        rsv[r] = vslot[r] - a;
+                    }
+                }
+            }
+            __syncwarp();
+            // phase B
+            double xn[RS];
+            if (P > 1) {
+                double v = 0.0;
+                if (rowok) {
+                    const double *Dr = st + oD + rowoff;
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) if (c0 + c < B) v = fma(Dr[c0 + c], rsv[c0 + c], v);
+                }
+                xn[0] = v;
+#pragma unroll
+                for (int o = 1; o < P; ++o) xn[0] += __shfl_down_sync(0xffffffffu, v, o);
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < RS; ++sl) {
+                    const int r = lane + 32 * sl;
+                    xn[sl] = (r < B) ? skew_dot<B>(st + oD + r * B, rsv, q) : 0.0;
+                }
+            }
+            if (succ == 1 && s_prog[w + 1] < idx - RING + 1) {
+                int spin = 0;
+                while (s_prog[w + 1] < idx - RING + 1) {
+                    __nanosleep(40);
+                    if (++spin > kSpinLimit) { if (lane == 0) atomicExch(err, 2); return; }
+                }
+            }
+#pragma unroll
+            for (int sl = 0; sl < RS; ++sl) {
+                const int r = P > 1 ? r0 : lane + 32 * sl;
+                const bool own = (P > 1) ? own1 : (r < B);
+                if (own) {
+                    double v = xn[sl];
+                    if (omega != 1.0) v = omega * v + (1.0 - omega) * __ldcg(x + (size_t)e * B + r);
+                    __stcg(x + (size_t)e * B + r, v);
+                    xprev[r] = v;
+                    if (succ == 1) ring[rg * BP + r] = v;
+                    if (succ == 2) __stcg(mbox + (size_t)e * B + r, v);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (succ == 1)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hand_a + 8u * (uint32_t)rg) : "memory");
+                s_prog[w] = idx + 1;
+                if (idx + S < Ni) {
+                    fence_proxy_async();
+                    issue_a(idx + S);
+                }
+            }
+            prefetch_vectors(idx + D);
+            if (pred == 2) {
+                have_pv = pred_ready_global(e + dir + pred_off, PVn);
+#pragma unroll
+                for (int sl = 0; sl < RS; ++sl) PV[sl] = PVn[sl];
+            }
+            // advance the counters
+            e_prev = e;
+            e += dir;
+            shift ^= flip;
+            if (++s == S) { s = 0; ph ^= 1; }
+            if (++rg == RING) { rg = 0; rph ^= 1; }
+            if (++vi == D + 1) vi = 0;
         }
+        if (idx < Ni) cur = elem_at(dir > 0 ? idx : Ni - 1 - idx);
     }
+    for (; idx < Ni; ++idx)
+        if (!generic_step(idx)) return;
+    cp_async_wait<0>();
 }
 
 // structure check: BSR (indices, indptr) == closed-form 5-point stencil?
@@ -655,20 +937,29 @@ int stream_launch(int mode, int b, const double *data, const int32_t *indices, c
     return 0;
 }
 
-template <int B>
-static int gs_rows_launch_t(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
+template <int B, int WW, int SS>
+static int gs_rows_launch_c(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
                             double omega, const int32_t *skip, cudaStream_t st) {
-    using C = GsCfg<B>;
+    using C = GsCfg<B, WW, SS>;
     static bool configured = false;
     if (!configured) {
-        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_rows<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_rows<B, WW, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM));
         configured = true;
     }
     DGB_CUDA_OK(cudaMemsetAsync(g_work, 0, sizeof(int), st));
     const int grid = (S_.Nj + C::W - 1) / C::W;
-    k_gs_rows<B><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, g_work, g_err, skip);
+    k_gs_rows<B, WW, SS><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, g_work, g_err, skip);
     DGB_LAUNCH_OK();
     return 0;
+}
+int g_gs_variant = 0;   // experiment switch (DGB_GS_VARIANT)
+template <int B>
+static int gs_rows_launch_t(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
+                            double omega, const int32_t *skip, cudaStream_t st) {
+    if (B == 9 && g_gs_variant == 1) return gs_rows_launch_c<9, 8, 6>(gs, rhs, x, mbox, S_, dir, omega, skip, st);
+    if (B == 9 && g_gs_variant == 2) return gs_rows_launch_c<9, 4, 12>(gs, rhs, x, mbox, S_, dir, omega, skip, st);
+    return gs_rows_launch_c<B, GsDefault<B>::W, GsDefault<B>::S>(gs, rhs, x, mbox, S_, dir, omega, skip, st);
 }
 
 int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double *mbox, int Ni, int Nj, int flags,
@@ -689,6 +980,7 @@ extern "C" {
 int dgb_set_kernel_path(int32_t path) {
     const int old = g_kernel_path;
     if (path == 0 || path == 1) g_kernel_path = path;
+    if (path >= 100) g_gs_variant = path - 100;      // tuning experiments only
     return old;
 }
 
