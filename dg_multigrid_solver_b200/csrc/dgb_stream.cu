@@ -342,12 +342,18 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         fence_proxy_async();
     }
     __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // opaque to the compiler from here on: keep them in registers (ptxas otherwise re-derives every
+    // shared-memory address from SR_TID in the latency-critical element loop)
+    asm volatile("" : "+r"(w));
+    asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, Nj = S_.Nj;
     const int sr = s_ticket * W + w;           // row index in sweep order
     if (sr >= Nj) return;
     const int j = dir > 0 ? sr : Nj - 1 - sr;
-    double *wbase = reinterpret_cast<double *>(smem) + (size_t)w * C::WARP_D;
+    uint32_t woff = (uint32_t)w * (uint32_t)(C::WARP_D * sizeof(double));
+    asm volatile("" : "+r"(woff));
+    double *wbase = reinterpret_cast<double *>(smem + woff);
     double *vs = wbase + S * C::STAGE_D;       // [5][BP]  directly loaded neighbour vectors (wrap cases)
     double *xprev = vs + 5 * BP;               // previous element of this row (new value)
     double *rsv = xprev + BP;                  // rhs - sum offdiag
@@ -700,10 +706,11 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     if (!generic_step(0)) return;
     idx = 1;
     if (fast_ok) {
-        // loop-carried counters instead of idx % / idx / arithmetic
+        // loop-carried counters / running pointers instead of idx % , idx / and address arithmetic
         int s = 1 % S, ph = (1 / S) & 1;                   // TMA stage and its parity
         int rg = 1 % RING, rph = (1 / RING) & 1;           // hand-over ring slot and parity
-        int vi = 1 % (D + 1);                              // vector ring slot
+        int vi = 1 % (D + 1);                              // vector ring slot of the current element
+        int vp = (1 + D) % (D + 1);                        // vector ring slot being prefetched (element idx + D)
         int e = j * Ni + (dir > 0 ? 1 : Ni - 2);
         int shift = (int)((k0_of(dir > 0 ? 1 : Ni - 2) * B2) & 1);
         const int flip = (n_int & B2) & 1;
@@ -711,6 +718,13 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         const int rowoff = (P > 1 ? r0 : 0) * B;
         const bool rowok = P > 1 ? (r0 < B) : true;
         const bool own1 = P > 1 && part == 0 && r0 < B;
+        // vector streams of element idx + D (lane c < B moves entry c; RS == 1 in the lean path for B <= 32)
+        const int step = dir * B;
+        const double *p_rhs = rhs + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D)) * B + lane;
+        const double *p_side = x + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D) + dir) * B + lane;
+        const double *p_next = x + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D) + dir * Ni) * B + lane;
+        // TMA source of element idx + S
+        long long k_issue = k0_of(dir > 0 ? 1 + S : Ni - 2 - S);      // only meaningful while idx + S < Ni
         for (; idx <= Ni - 2; ++idx) {
             // predecessor-row value
             if (pred == 1) {
@@ -827,11 +841,47 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hand_a + 8u * (uint32_t)rg) : "memory");
                 s_prog[w] = idx + 1;
                 if (idx + S < Ni) {
+                    // element idx + S: interior unless it is the last of the sweep
+                    const int cnt = (idx + S == Ni - 1) ? (dir > 0 ? n_last : n_first) : n_int;
+                    const size_t byte0 = (size_t)k_issue * B2 * 8, byte1 = byte0 + (size_t)cnt * B2 * 8;
+                    const size_t a0 = byte0 & ~(size_t)15, a1 = (byte1 + 15) & ~(size_t)15;
+                    const uint32_t bar = full_a + 8u * (uint32_t)s;          // same stage as the one just consumed
+                    const uint32_t dst = stage_a + (uint32_t)(s * C::STAGE_D * 8);
+                    const uint32_t bytes = (uint32_t)(a1 - a0);
                     fence_proxy_async();
-                    issue_a(idx + S);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                        "l"(gbytes + a0), "r"(bytes), "r"(bar)
+                        : "memory");
                 }
             }
-            prefetch_vectors(idx + D);
+            // next TMA source: fwd: += count of the element just issued; bwd: -= count of the one before it
+            if (dir > 0) k_issue += (idx + S == Ni - 1) ? n_last : n_int;
+            else k_issue -= (idx + S + 1 == Ni - 1) ? n_first : n_int;
+            // prefetch the vector streams of element idx + D into the slot of element idx - 1
+            if (idx + D < Ni) {
+                double *slot = vring + vp * (3 * BP);
+                if (RS == 1) {
+                    if (lane < B) {
+                        cp_async8(slot + lane, p_rhs);
+                        if (idx + D < Ni - 1) cp_async8(slot + BP + lane, p_side);     // not for the last element of the row
+                        if (next_row_ok) cp_async8(slot + 2 * BP + lane, p_next);
+                    }
+                } else {
+#pragma unroll
+                    for (int sl = 0; sl < RS; ++sl) {
+                        const int c = lane + 32 * sl;
+                        if (c < B) {
+                            cp_async8(slot + c, p_rhs + 32 * sl);
+                            if (idx + D < Ni - 1) cp_async8(slot + BP + c, p_side + 32 * sl);
+                            if (next_row_ok) cp_async8(slot + 2 * BP + c, p_next + 32 * sl);
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+            p_rhs += step; p_side += step; p_next += step;
             if (pred == 2) {
                 have_pv = pred_ready_global(e + dir + pred_off, PVn);
 #pragma unroll
@@ -844,6 +894,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             if (++s == S) { s = 0; ph ^= 1; }
             if (++rg == RING) { rg = 0; rph ^= 1; }
             if (++vi == D + 1) vi = 0;
+            if (++vp == D + 1) vp = 0;
         }
         if (idx < Ni) cur = elem_at(dir > 0 ? idx : Ni - 1 - idx);
     }
