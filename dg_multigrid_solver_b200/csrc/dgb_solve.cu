@@ -339,6 +339,7 @@ k_prolong_add(int kind, const double *__restrict__ P, int nc, int nf, int Nj_c, 
 namespace dgb {
 // streaming kernels (dgb_stream.cu)
 extern int g_kernel_path;
+extern int g_kstream_min_b;
 bool stream_supported(int b);
 int stream_launch(int mode, int b, const double *data, const int32_t *indices, const int32_t *indptr, int N,
                   int Ni, const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
@@ -347,9 +348,14 @@ int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double
                    int dir, double omega, const int32_t *skip, cudaStream_t st);
 enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
 
+// kernels that need the closed-form DG stencil (k_gs_rows)
 static bool use_stream(const dgb_operator *op) {
     return g_kernel_path == 0 && op->stencil >= 0 && stream_supported(op->b);
 }
+// k_stream (apply / residual / Jacobi / colour sweeps): measured on B200 the row-per-thread kernels win for
+// small blocks (b <= 9: their strided row reads are still served by the L1; profiles/r01_probe1_*.jsonl),
+// the TMA-staged kernel for the larger ones
+static bool use_kstream(const dgb_operator *op) { return use_stream(op) && op->b >= g_kstream_min_b; }
 static int check_op(const dgb_operator *op) {
     DGB_ARG(op != nullptr);
     DGB_ARG(op->data && op->indices && op->indptr && op->Ni > 0 && op->Nj > 0 && op->b > 0);
@@ -380,7 +386,7 @@ int dgb_bsr_apply(const dgb_operator *op, const double *x, double *y, void *stre
     DGB_ARG(x && y);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
-    if (use_stream(op))
+    if (use_kstream(op))
         return stream_launch(S_APPLY, op->b, op->data, op->indices, op->indptr, N, op->Ni, nullptr, x, y, nullptr,
                              1.0, -1, nullptr, st, nullptr);
     Sel sel{0, 0, N, 1, 0, N};
@@ -398,7 +404,7 @@ int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x,
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     int grid = 1;
-    if (use_stream(op)) {
+    if (use_kstream(op)) {
         rc = stream_launch(S_RESIDUAL, op->b, op->data, op->indices, op->indptr, N, op->Ni, rhs, x, r, partials, 1.0,
                            -1, skip, st, &grid);
         if (rc) return rc;
@@ -494,7 +500,7 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
-            if (use_stream(op) && op->gs_data != nullptr) {
+            if (use_kstream(op) && op->gs_data != nullptr) {
                 rc = stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x, x, nullptr,
                                    1.0, colour, skip, st, nullptr);
             } else {
@@ -516,7 +522,7 @@ int dgb_block_relax_sweep(const dgb_operator *op, const double *rhs, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     if (x_in == x_out) return lexicographic_pass(op, rhs, x_out, omega, +1, nullptr, st);
-    if (use_stream(op) && op->gs_data != nullptr)
+    if (use_kstream(op) && op->gs_data != nullptr)
         return stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x_in, x_out,
                              nullptr, omega, -1, nullptr, st, nullptr);
     Sel sel{0, 0, op->Ni, op->Nj, 0, N};

@@ -928,6 +928,7 @@ static int *g_work = nullptr;      // [0] ticket, [1..] progress
 static int g_work_cap = 0;
 static int *g_err = nullptr;       // device-side error flag of the async kernels
 int g_kernel_path = 0;             // 0 auto (streaming kernels where available), 1 generic only
+int g_kstream_min_b = 1000;        // k_stream v1 loses to the row-per-thread kernels for every b measured (profiles/r01_probe10); off by default (tuning: dgb_set_kernel_path(200 + b))
 
 static int ensure_work(int n_rows) {
     if (g_err == nullptr) {
@@ -1031,7 +1032,8 @@ extern "C" {
 int dgb_set_kernel_path(int32_t path) {
     const int old = g_kernel_path;
     if (path == 0 || path == 1) g_kernel_path = path;
-    if (path >= 100) g_gs_variant = path - 100;      // tuning experiments only
+    if (path >= 100 && path < 200) g_gs_variant = path - 100;      // tuning experiments only
+    if (path >= 200) g_kstream_min_b = path - 200;
     return old;
 }
 

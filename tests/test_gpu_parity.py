@@ -113,6 +113,7 @@ def test_streaming_kernels_match_generic_kernels(name):
     L = _lib.load()
     rng = np.random.default_rng(11)
     try:
+        L.dgb_set_kernel_path(200 + 1)          # k_stream for every block size (default: b >= 16 only)
         for grid in d.grids:
             assert grid.stencil >= 0 and grid.d_gs is not None
             n = grid.d_rhs.numel()
@@ -143,6 +144,7 @@ def test_streaming_kernels_match_generic_kernels(name):
                     assert float((got - ref).abs().max()) <= 1e-12 * scale, (name, grid.Ni, grid.b, key)
     finally:
         L.dgb_set_kernel_path(0)
+        L.dgb_set_kernel_path(200 + 1000)
 
 
 def test_block_diag_inverse_and_transfers():

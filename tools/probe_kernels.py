@@ -72,6 +72,8 @@ def main():
         "redblack": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, 1, 1, None, st), ab["gs_pass"]),
         "jacobi": (lambda: _lib.call("dgb_block_relax_sweep", op, g.d_rhs, x, y, 1.0, st), ab["gs_pass"]),
     }
+    if os.environ.get("DGB_KSTREAM_MIN_B"):
+        L.dgb_set_kernel_path(200 + int(os.environ["DGB_KSTREAM_MIN_B"]))
     if os.environ.get("DGB_GS_VARIANT"):
         L.dgb_set_kernel_path(100 + int(os.environ["DGB_GS_VARIANT"]))
     for path, nm in ((0, "stream"), (1, "generic")):
