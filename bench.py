@@ -338,10 +338,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2048, help="elements per direction (BASELINE configs[2]: 2048)")
     ap.add_argument("--p", type=int, default=2)
-    ap.add_argument("--gs-mode", default="lexicographic", choices=["lexicographic", "redblack"])
+    ap.add_argument("--gs-mode", default="lexicographic", choices=["lexicographic", "redblack", "slab_lexicographic"])
     ap.add_argument("--check-residual", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-multi", action="store_true",
+                    help="N>1: keep the exact global lexicographic order (slabs sweep one after the other)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

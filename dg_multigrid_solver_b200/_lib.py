@@ -57,7 +57,7 @@ class TablesDesc(ctypes.Structure):
 GS_LEXICOGRAPHIC, GS_REDBLACK = 0, 1
 TRANSFER_P, TRANSFER_H = 1, 2
 SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_seidel": 2}
-FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV = 1, 2, 4
+FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV, FLAG_GHOST_LO, FLAG_GHOST_HI = 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); every symbol include/dgb200.h declares
 OP = ctypes.POINTER(Operator)
@@ -76,12 +76,15 @@ SIGNATURES = {
     "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_check_stencil": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_pass": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_gs_colour": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_relax_sweep": (c_i32, [OP, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "dgb_smoother_check": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "dgb_block_gauss_seidel_pyamg": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_restrict": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_prolong_add": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_restrict_slab": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_prolong_add_slab": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_vcycle": (c_i32, [ctypes.POINTER(Level), c_i32, ctypes.POINTER(VcycleOpts), c_vp, c_vp, c_vp, c_vp]),
     "dgb_tables_create": (c_i32, [ctypes.POINTER(TablesDesc), ctypes.POINTER(c_vp)]),
     "dgb_tables_destroy": (None, [c_vp]),

@@ -214,6 +214,13 @@ k_assemble_poisson(TabView T, const double *__restrict__ vol, const double *__re
     const int N = S.Ni * S.Nj;
     for (int e = blockIdx.x; e < N; e += gridDim.x) {
         const int i = e % S.Ni, j = e / S.Ni;
+        if (!S.active(j)) {       // ghost row of a slab: an empty matrix row
+            if (tid == 0) {
+                indptr[e] = (int32_t)S.row_start(i, j);
+                if (e == N - 1) indptr[N] = (int32_t)S.row_start(0, S.Nj);
+            }
+            continue;
+        }
         if (tid == 0) {
             int c[5], rk[5];
             S.cols(i, j, c);
@@ -365,6 +372,10 @@ k_assemble_rhs(TabView T, const double *__restrict__ vol, const double *__restri
     const int k = threadIdx.x;
     for (int e = blockIdx.x; e < N; e += gridDim.x) {
         const int i = e % S.Ni, j = e / S.Ni;
+        if (!S.active(j)) {
+            if (k < b) rhs[(size_t)e * b + k] = 0.0;
+            continue;
+        }
         int c[5];
         S.cols(i, j, c);
         if (k < b) {
@@ -481,7 +492,7 @@ int dgb_metrics(const dgb_tables *t, const double *xn, const double *yn, int32_t
 }
 
 int64_t dgb_poisson_nnzb(int32_t Ni, int32_t Nj, int32_t flags) {
-    Stencil S{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
+    Stencil S = make_stencil(Ni, Nj, flags);
     return S.row_start(0, Nj);
 }
 
@@ -494,7 +505,7 @@ int dgb_assemble_poisson(const dgb_tables *t, const double *vol, const double *f
     DGB_ARG(dgb_poisson_nnzb(Ni, Nj, flags) < 2147483647LL);
     cudaStream_t st = (cudaStream_t)stream;
     TabView T = view(t);
-    Stencil S{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
+    Stencil S = make_stencil(Ni, Nj, flags);
     const size_t bb = (size_t)T.b * T.b;
     const size_t smem = sizeof(double) * (6 * bb + 2 * (size_t)T.nq * T.b + T.nq + 4 * T.nq1 +
                                           2 * 4 * (size_t)T.nq1 * T.b);
@@ -516,7 +527,7 @@ int dgb_assemble_rhs(const dgb_tables *t, const double *vol, const double *face,
     DGB_ARG(t->b <= 64);
     cudaStream_t st = (cudaStream_t)stream;
     TabView T = view(t);
-    Stencil S{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
+    Stencil S = make_stencil(Ni, Nj, flags);
     int64_t g = (int64_t)Ni * Nj;
     if (g > sm_count() * 32) g = sm_count() * 32;
     k_assemble_rhs<<<(int)g, 64, 0, st>>>(T, vol, face, area, minv, f_vol, g_face, S, nu, sigma,

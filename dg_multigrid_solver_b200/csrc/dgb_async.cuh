@@ -72,15 +72,19 @@ __device__ __forceinline__ void named_bar_sync() {
 //  periodic wrap in i for O-grids, in i and j for fully periodic grids, columns ascending)
 struct Stencil {
     int Ni, Nj, per_i, per_j;
+    int ja0, ja1;   // active element rows [ja0, ja1): rows outside are ghost rows of a slab (no matrix rows)
+    __host__ __device__ bool active(int j) const { return j >= ja0 && j < ja1; }
     __host__ __device__ int bj(int j) const { return per_j ? 0 : ((j == 0) + (j == Nj - 1)); }
     __host__ __device__ int count(int i, int j) const {
-        return 5 - bj(j) - (per_i ? 0 : ((i == 0) + (i == Ni - 1)));
+        return active(j) ? 5 - bj(j) - (per_i ? 0 : ((i == 0) + (i == Ni - 1))) : 0;
     }
     __host__ __device__ long long row_start(int i, int j) const {
-        // blocks in all element rows j' < j, then in (i' < i, j)
-        const int nbrows = per_j ? 0 : ((j > 0) + (j >= Nj));
-        long long s = (long long)j * (5 * (long long)Ni - (per_i ? 0 : 2)) - (long long)Ni * nbrows;
-        if (j < Nj) s += (long long)i * (5 - bj(j)) - ((per_i || i == 0) ? 0 : 1);
+        if (j < ja0) return 0;
+        const int jj = j < ja1 ? j : ja1;
+        // blocks in the active element rows [ja0, jj), then in (i' < i, jj)
+        const int nbrows = per_j ? 0 : ((ja0 == 0 && jj > 0) + (ja1 == Nj && jj >= Nj));
+        long long s = (long long)(jj - ja0) * (5 * (long long)Ni - (per_i ? 0 : 2)) - (long long)Ni * nbrows;
+        if (j < ja1) s += (long long)i * (5 - bj(j)) - ((per_i || i == 0) ? 0 : 1);
         return s;
     }
     // neighbour element index per slot {m, iL, iR, jL, jR} (-1 = Dirichlet boundary)
@@ -93,6 +97,16 @@ struct Stencil {
         c[4] = j < Nj - 1 ? m + Ni : (per_j ? i : -1);
     }
 };
+// flags: DGB_FLAG_PERIODIC_I|J, DGB_FLAG_GHOST_LO|HI (include/dgb200.h)
+__host__ __device__ inline Stencil make_stencil(int Ni, int Nj, int flags) {
+    Stencil S;
+    S.Ni = Ni; S.Nj = Nj;
+    S.per_i = (flags & 1) ? 1 : 0;
+    S.per_j = (flags & 2) ? 1 : 0;
+    S.ja0 = (flags & 8) ? 1 : 0;
+    S.ja1 = Nj - ((flags & 16) ? 1 : 0);
+    return S;
+}
 
 // rank of each present slot in ascending column order; ties keep slot order (python's stable
 // sorted(), dgfem/discrete_system.py:137-138)

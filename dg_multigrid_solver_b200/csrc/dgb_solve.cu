@@ -43,9 +43,9 @@ struct Sel {
 
 __device__ __forceinline__ int sel_element(const Sel &s, int idx) {
     if (s.mode == 0) return idx;
-    if (s.mode == 1) {
+    if (s.mode == 1) {     // colour class; i_lo doubles as a parity shift (global row offset of a slab)
         const int i = idx % s.Ni, j = idx / s.Ni;
-        return (((i + j) & 1) == s.sel) ? idx : -1;
+        return (((i + j + s.i_lo) & 1) == s.sel) ? idx : -1;
     }
     const int i = s.i_lo + idx;
     return (s.sel - i) * s.Ni + i;
@@ -84,6 +84,7 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
         double acc = 0.0;
         if (e >= 0) {
             const int j0 = indptr[e], j1 = indptr[e + 1];
+            if (j0 == j1) e = -1;        // empty block row (ghost row of a slab): not part of this rank's operator
             for (int jj = j0; jj < j1; ++jj) {
                 const int col = indices[jj];
                 if (MODE == MODE_RELAX && col == e) continue;
@@ -189,6 +190,10 @@ k_block_diag_inverse(const double *__restrict__ data, const int32_t *__restrict_
     const int e = blockIdx.x * WPB + w;
     if (e >= n_brow) return;
     double *a = s_a[w];
+    if (indptr[e] == indptr[e + 1]) {       // empty (ghost) row
+        for (int t = lane; t < B * B; t += 32) dinv[(size_t)e * B * B + t] = 0.0;
+        return;
+    }
     // gather (sum of) the diagonal block(s) of row e
     for (int t = lane; t < B * B; t += 32) a[t] = 0.0;
     __syncwarp();
@@ -284,17 +289,30 @@ __device__ __forceinline__ size_t h_fine_elem(int K, int child, int Nj_c) {
     return (size_t)A0 * (4 * (size_t)Nj_c) + (size_t)a1 * (2 * (size_t)Nj_c) + 2 * (size_t)A2 + a3;
 }
 
+// Slab variant (kind DGB_TRANSFER_H_SLAB): children of coarse element (I, J) are the fine elements
+// (2I+a_i, 2J+a_j), child slot a_j*2+a_i -- what the reference's gather means on the square global grid --
+// with ghost-row offsets: coarse rows [gc, Nj_c - gc_hi) are active, fine row = gf + 2*(J - gc) + a_j.
+struct SlabH {
+    int Ni_c, gc, gf;     // coarse elements per row, ghost rows below on the coarse / fine level
+};
+__device__ __forceinline__ size_t slab_fine_elem(int K, int child, SlabH h) {
+    const int J = K / h.Ni_c, I = K - J * h.Ni_c;
+    const int aj = child >> 1, ai = child & 1;
+    return (size_t)(h.gf + 2 * (J - h.gc) + aj) * (2 * (size_t)h.Ni_c) + 2 * (size_t)I + ai;
+}
+
 __global__ void __launch_bounds__(256)
 k_restrict(int kind, const double *__restrict__ R, int nc, int nf, int Nj_c, int64_t n_coarse_el,
-           const double *__restrict__ fine, double *__restrict__ coarse) {
+           const double *__restrict__ fine, double *__restrict__ coarse, SlabH slab, int64_t first_el) {
     extern __shared__ double s_R[];
     for (int t = threadIdx.x; t < nc * nf; t += blockDim.x) s_R[t] = R[t];
     __syncthreads();
     const int64_t total = n_coarse_el * nc;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-         o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t K = o / nc;
-        const int a = (int)(o - K * nc);
+    for (int64_t o0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o0 < total;
+         o0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = o0 / nc + first_el;           // first_el: first active coarse element of a slab
+        const int a = (int)(o0 % nc);
+        const int64_t o = K * nc + a;
         double acc = 0.0;
         if (kind == DGB_TRANSFER_P) {
             const double *f = fine + K * nf;
@@ -302,7 +320,8 @@ k_restrict(int kind, const double *__restrict__ R, int nc, int nf, int Nj_c, int
         } else {
             const int bf = nf / 4;
             for (int child = 0; child < 4; ++child) {
-                const double *f = fine + h_fine_elem((int)K, child, Nj_c) * bf;
+                const size_t fe = kind == DGB_TRANSFER_H ? h_fine_elem((int)K, child, Nj_c) : slab_fine_elem((int)K, child, slab);
+                const double *f = fine + fe * bf;
                 for (int d = 0; d < bf; ++d) acc = fma(s_R[a * nf + child * bf + d], f[d], acc);
             }
         }
@@ -312,24 +331,25 @@ k_restrict(int kind, const double *__restrict__ R, int nc, int nf, int Nj_c, int
 
 __global__ void __launch_bounds__(256)
 k_prolong_add(int kind, const double *__restrict__ P, int nc, int nf, int Nj_c, int64_t n_coarse_el,
-              const double *__restrict__ coarse, double *__restrict__ fine) {
+              const double *__restrict__ coarse, double *__restrict__ fine, SlabH slab, int64_t first_el) {
     extern __shared__ double s_P[];
     for (int t = threadIdx.x; t < nc * nf; t += blockDim.x) s_P[t] = P[t];
     __syncthreads();
     const int64_t total = n_coarse_el * nf;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total;
-         o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t K = o / nf;
-        const int f = (int)(o - K * nf);
+    for (int64_t o0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o0 < total;
+         o0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t K = o0 / nf + first_el;
+        const int f = (int)(o0 % nf);
         const double *uc = coarse + K * nc;
         double acc = 0.0;
         for (int a = 0; a < nc; ++a) acc = fma(s_P[f * nc + a], uc[a], acc);
         if (kind == DGB_TRANSFER_P) {
-            fine[o] += acc;
+            fine[K * nf + f] += acc;
         } else {
             const int bf = nf / 4;
             const int child = f / bf, d = f - child * bf;
-            fine[h_fine_elem((int)K, child, Nj_c) * bf + d] += acc;
+            const size_t fe = kind == DGB_TRANSFER_H ? h_fine_elem((int)K, child, Nj_c) : slab_fine_elem((int)K, child, slab);
+            fine[fe * bf + d] += acc;
         }
     }
 }
@@ -514,6 +534,15 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     return lexicographic_pass(op, rhs, x, 1.0, direction, skip, st);
 }
 
+int dgb_block_gs_colour(const dgb_operator *op, const double *rhs, double *x, int32_t colour, int32_t shift,
+                        const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && rhs && x && (colour == 0 || colour == 1));
+    Sel sel{1, colour, op->Ni, op->Nj, shift & 1, op->Ni * op->Nj};
+    return relax_launch(op, rhs, x, x, 1.0, sel, skip, (cudaStream_t)stream);
+}
+
 int dgb_block_relax_sweep(const dgb_operator *op, const double *rhs, const double *x_in,
                           double *x_out, double omega, void *stream) {
     int rc = check_op(op);
@@ -577,30 +606,52 @@ int dgb_block_gauss_seidel_pyamg(const dgb_operator *op, const double *rhs, doub
     return 0;
 }
 
-int dgb_restrict(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c,
-                 int32_t Nj_c, const double *fine, double *coarse, void *stream) {
-    DGB_ARG(R && fine && coarse && nc > 0 && nf > 0 && Ni_c > 0 && Nj_c > 0);
-    DGB_ARG(kind == DGB_TRANSFER_P || (kind == DGB_TRANSFER_H && nf % 4 == 0));
-    const int64_t nel = (int64_t)Ni_c * Nj_c;
-    int64_t g = (nel * nc + 255) / 256;
+static int transfer_launch(bool restrict_dir, int32_t kind, const double *M, int32_t nc, int32_t nf, int32_t Ni_c,
+                           int32_t Nj_c, int32_t ghost_c_lo, int32_t ghost_c_hi, int32_t ghost_f_lo,
+                           const double *src, double *dst, void *stream) {
+    DGB_ARG(M && src && dst && nc > 0 && nf > 0 && Ni_c > 0 && Nj_c > 0);
+    DGB_ARG(kind == DGB_TRANSFER_P || ((kind == DGB_TRANSFER_H || kind == DGB_TRANSFER_H_SLAB) && nf % 4 == 0));
+    DGB_ARG(ghost_c_lo >= 0 && ghost_c_hi >= 0 && Nj_c - ghost_c_lo - ghost_c_hi > 0);
+    // only the active coarse rows are written / read (ghost rows of a slab belong to the neighbour rank)
+    const int64_t nel = (int64_t)Ni_c * (Nj_c - ghost_c_lo - ghost_c_hi);
+    const int64_t first = (int64_t)Ni_c * ghost_c_lo;
+    SlabH slab{Ni_c, ghost_c_lo, ghost_f_lo};
+    int64_t g = (nel * (restrict_dir ? nc : nf) + 255) / 256;
     if (g > sm_count() * 16) g = sm_count() * 16;
-    k_restrict<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, R, nc, nf, Nj_c, nel,
-                                                                              fine, coarse);
+    if (restrict_dir)
+        k_restrict<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, M, nc, nf, Nj_c, nel, src, dst,
+                                                                                  slab, first);
+    else
+        k_prolong_add<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, M, nc, nf, Nj_c, nel, src,
+                                                                                     dst, slab, first);
     DGB_LAUNCH_OK();
     return 0;
 }
 
+int dgb_restrict(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c,
+                 int32_t Nj_c, const double *fine, double *coarse, void *stream) {
+    DGB_ARG(kind == DGB_TRANSFER_P || kind == DGB_TRANSFER_H);
+    return transfer_launch(true, kind, R, nc, nf, Ni_c, Nj_c, 0, 0, 0, fine, coarse, stream);
+}
+
 int dgb_prolong_add(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c,
                     int32_t Nj_c, const double *coarse, double *fine, void *stream) {
-    DGB_ARG(P && fine && coarse && nc > 0 && nf > 0 && Ni_c > 0 && Nj_c > 0);
-    DGB_ARG(kind == DGB_TRANSFER_P || (kind == DGB_TRANSFER_H && nf % 4 == 0));
-    const int64_t nel = (int64_t)Ni_c * Nj_c;
-    int64_t g = (nel * nf + 255) / 256;
-    if (g > sm_count() * 16) g = sm_count() * 16;
-    k_prolong_add<<<(int)g, 256, sizeof(double) * nc * nf, (cudaStream_t)stream>>>(kind, P, nc, nf, Nj_c,
-                                                                                 nel, coarse, fine);
-    DGB_LAUNCH_OK();
-    return 0;
+    DGB_ARG(kind == DGB_TRANSFER_P || kind == DGB_TRANSFER_H);
+    return transfer_launch(false, kind, P, nc, nf, Ni_c, Nj_c, 0, 0, 0, coarse, fine, stream);
+}
+
+int dgb_restrict_slab(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c, int32_t Nj_c,
+                      int32_t ghost_c_lo, int32_t ghost_c_hi, int32_t ghost_f_lo, const double *fine,
+                      double *coarse, void *stream) {
+    return transfer_launch(true, kind == DGB_TRANSFER_H ? DGB_TRANSFER_H_SLAB : kind, R, nc, nf, Ni_c, Nj_c,
+                           ghost_c_lo, ghost_c_hi, ghost_f_lo, fine, coarse, stream);
+}
+
+int dgb_prolong_add_slab(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c, int32_t Nj_c,
+                         int32_t ghost_c_lo, int32_t ghost_c_hi, int32_t ghost_f_lo, const double *coarse,
+                         double *fine, void *stream) {
+    return transfer_launch(false, kind == DGB_TRANSFER_H ? DGB_TRANSFER_H_SLAB : kind, P, nc, nf, Ni_c, Nj_c,
+                           ghost_c_lo, ghost_c_hi, ghost_f_lo, coarse, fine, stream);
 }
 
 }  // extern "C"

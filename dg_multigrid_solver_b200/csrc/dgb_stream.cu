@@ -277,8 +277,9 @@ struct GsCfg {
     static constexpr int STAGE_D = (5 * B2 + 2 + 1) & ~1;           // doubles per stage, even
     static constexpr int BP = (B + 1) & ~1;
     static constexpr int PD = 16 / gcd_c(B, 16);
-    // per warp: stages | vs[5] | xprev | rs | pvs | ring[RING] | vring[D+1][3]
-    static constexpr int WARP_D = S * STAGE_D + 8 * BP + RING * BP + (D + 1) * 3 * BP;
+    // per warp: stages | vs[5] | xprev | rs | pvs | ring[RING] | vring[D+1][4]
+    static constexpr int NV = 4;                                    // rhs | x side | x next row | x previous row (ghost)
+    static constexpr int WARP_D = S * STAGE_D + 8 * BP + RING * BP + (D + 1) * NV * BP;
     static constexpr size_t oBar = sizeof(double) * W * WARP_D;          // full[W][S], hand[W][RING]
     static constexpr size_t oProg = oBar + sizeof(uint64_t) * W * (S + RING);
     static constexpr size_t SMEM = oProg + sizeof(int) * W;
@@ -348,9 +349,10 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     asm volatile("" : "+r"(w));
     asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, Nj = S_.Nj;
+    const int nrows = S_.ja1 - S_.ja0;         // active element rows (ghost rows of a slab are only read)
     const int sr = s_ticket * W + w;           // row index in sweep order
-    if (sr >= Nj) return;
-    const int j = dir > 0 ? sr : Nj - 1 - sr;
+    if (sr >= nrows) return;
+    const int j = dir > 0 ? S_.ja0 + sr : S_.ja1 - 1 - sr;
     uint32_t woff = (uint32_t)w * (uint32_t)(C::WARP_D * sizeof(double));
     asm volatile("" : "+r"(woff));
     double *wbase = reinterpret_cast<double *>(smem + woff);
@@ -359,7 +361,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     double *rsv = xprev + BP;                  // rhs - sum offdiag
     double *pvs = rsv + BP;                    // predecessor-row value when it came through the mailbox
     double *ring = pvs + BP;                   // [RING][BP], written by this warp, read by warp w+1
-    double *vring = ring + RING * BP;          // [D+1][3][BP]: rhs | x side | x next row
+    double *vring = ring + RING * BP;          // [D+1][NV][BP]: rhs | x side | x next row | x previous row (old)
     const double *ring_pred = ring - C::WARP_D;
     uint64_t *full = bars + w * (S + RING);    // TMA stage barriers of this warp
     uint64_t *hand = full + S;                 // hand[slot]: this warp has written ring slot `slot`
@@ -404,12 +406,15 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         for (int idx = 0; idx < S && idx < Ni; ++idx) issue(idx);
     const int jn = j + dir;                                  // next row in sweep order (old values)
     const bool next_row_ok = jn >= 0 && jn < Nj;
+    // previous row holds OLD values when this row starts a sweep inside a slab (ghost row of the neighbour slab)
+    const bool prev_row_old = (sr == 0) && (j - dir >= 0) && (j - dir < Nj);
+    constexpr int NV = C::NV;
     // cp.async prefetch of the sequential vector streams for sweep index n (one commit per call)
     auto prefetch_vectors = [&](int n) {
         if (n < Ni) {
             const int i = dir > 0 ? n : Ni - 1 - n;
             const int e = j * Ni + i;
-            double *slot = vring + (size_t)(n % (D + 1)) * 3 * BP;
+            double *slot = vring + (size_t)(n % (D + 1)) * NV * BP;
             const int iside = i + dir;
 #pragma unroll
             for (int sl = 0; sl < RS; ++sl) {
@@ -418,6 +423,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                     cp_async8(slot + c, rhs + (size_t)e * B + c);
                     if (iside >= 0 && iside < Ni) cp_async8(slot + BP + c, x + (size_t)(e + dir) * B + c);
                     if (next_row_ok) cp_async8(slot + 2 * BP + c, x + (size_t)(e + dir * Ni) * B + c);
+                    if (prev_row_old) cp_async8(slot + 3 * BP + c, x + (size_t)(e - dir * Ni) * B + c);
                 }
             }
         }
@@ -432,7 +438,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
     const int q = (lane & 15) / C::PD;
     // hand-over topology
     const int pred = sr == 0 ? 0 : (w > 0 ? 1 : 2);                       // 0 none, 1 smem ring, 2 global mailbox
-    const int succ = sr == Nj - 1 ? 0 : (w < W - 1 ? 1 : 2);
+    const int succ = sr == nrows - 1 ? 0 : (w < W - 1 ? 1 : 2);
     const int pred_off = -dir * Ni;                                        // element offset to the predecessor row
     const double sentinel = __longlong_as_double(-1LL);
 
@@ -472,7 +478,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             if (t < tmpl.n && t != tD) {
                 const int off = tmpl.col[t];
                 if (off == -dir) tV = t;                                   // previous element (new value)
-                else if (pred != 0 && off == pred_off) tP = t;             // predecessor row (new value)
+                else if ((pred != 0 || prev_row_old) && off == pred_off) tP = t;   // previous row (new value, or ghost)
                 else if (off == dir) tS = t;                               // next element of the row (old)
                 else if (next_row_ok && off == dir * Ni) tN = t;           // next row (old)
                 else fast_ok = false;                                      // periodic wrap: generic path
@@ -529,7 +535,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         }
         // ---- vectors of this element have landed (cp.async groups complete in order) ----
         cp_async_wait<D - 1>();
-        const double *vslot = vring + (size_t)(idx % (D + 1)) * 3 * BP;
+        const double *vslot = vring + (size_t)(idx % (D + 1)) * NV * BP;
         if (pred == 2) {
 #pragma unroll
             for (int sl = 0; sl < RS; ++sl) {
@@ -537,10 +543,10 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                 if (c < B) pvs[c] = PV[sl];
             }
         }
-        const double *pvec = pred == 1 ? ring_pred + (idx % RING) * BP : pvs;
+        const double *pvec = pred == 1 ? ring_pred + (idx % RING) * BP : (pred == 2 ? pvs : vslot + 3 * BP);
         if (!fast) {
             // neighbour vectors that are neither streamed nor handed over (periodic wraps): load now
-            const int e_pred = pred ? e + pred_off : -2;
+            const int e_pred = (pred || prev_row_old) ? e + pred_off : -2;
             const int e_side = (i + dir >= 0 && i + dir < Ni) ? e + dir : -3;
             const int e_next = next_row_ok ? e + dir * Ni : -4;
 #pragma unroll
@@ -604,7 +610,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             }
         } else {
             tdiag = cur.tdiag;
-            const int e_pred = pred ? e + pred_off : -2;
+            const int e_pred = (pred || prev_row_old) ? e + pred_off : -2;
             const int e_side = (i + dir >= 0 && i + dir < Ni) ? e + dir : -3;
             const int e_next = next_row_ok ? e + dir * Ni : -4;
 #pragma unroll
@@ -723,6 +729,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
         const double *p_rhs = rhs + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D)) * B + lane;
         const double *p_side = x + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D) + dir) * B + lane;
         const double *p_next = x + (size_t)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D) + dir * Ni) * B + lane;
+        const double *p_pold = x + ((long long)(j * Ni + (dir > 0 ? 1 + D : Ni - 2 - D)) - (long long)dir * Ni) * B + lane;
         // TMA source of element idx + S
         long long k_issue = k0_of(dir > 0 ? 1 + S : Ni - 2 - S);      // only meaningful while idx + S < Ni
         for (; idx <= Ni - 2; ++idx) {
@@ -741,7 +748,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                 }
             }
             cp_async_wait<D - 1>();
-            const double *vslot = vring + vi * (3 * BP);
+            const double *vslot = vring + vi * (NV * BP);
             if (pred == 2) {
 #pragma unroll
                 for (int sl = 0; sl < RS; ++sl) {
@@ -749,7 +756,7 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                     if (c < B) pvs[c] = PV[sl];
                 }
             }
-            const double *pvec = pred == 1 ? ring_pred + rg * BP : pvs;
+            const double *pvec = pred == 1 ? ring_pred + rg * BP : (pred == 2 ? pvs : vslot + 3 * BP);
             if (!wait_a(full_a + 8u * (uint32_t)s, (uint32_t)ph)) return;
             const double *st = wbase + s * C::STAGE_D + shift;
             __syncwarp();
@@ -861,12 +868,13 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
             else k_issue -= (idx + S + 1 == Ni - 1) ? n_first : n_int;
             // prefetch the vector streams of element idx + D into the slot of element idx - 1
             if (idx + D < Ni) {
-                double *slot = vring + vp * (3 * BP);
+                double *slot = vring + vp * (NV * BP);
                 if (RS == 1) {
                     if (lane < B) {
                         cp_async8(slot + lane, p_rhs);
                         if (idx + D < Ni - 1) cp_async8(slot + BP + lane, p_side);     // not for the last element of the row
                         if (next_row_ok) cp_async8(slot + 2 * BP + lane, p_next);
+                        if (prev_row_old) cp_async8(slot + 3 * BP + lane, p_pold);
                     }
                 } else {
 #pragma unroll
@@ -876,12 +884,13 @@ k_gs_rows(const double *__restrict__ gs, const double *__restrict__ rhs, double 
                             cp_async8(slot + c, p_rhs + 32 * sl);
                             if (idx + D < Ni - 1) cp_async8(slot + BP + c, p_side + 32 * sl);
                             if (next_row_ok) cp_async8(slot + 2 * BP + c, p_next + 32 * sl);
+                            if (prev_row_old) cp_async8(slot + 3 * BP + c, p_pold + 32 * sl);
                         }
                     }
                 }
             }
             cp_async_commit();
-            p_rhs += step; p_side += step; p_next += step;
+            p_rhs += step; p_side += step; p_next += step; p_pold += step;
             if (pred == 2) {
                 have_pv = pred_ready_global(e + dir + pred_off, PVn);
 #pragma unroll
@@ -1000,7 +1009,7 @@ static int gs_rows_launch_c(const double *gs, const double *rhs, double *x, doub
         configured = true;
     }
     DGB_CUDA_OK(cudaMemsetAsync(g_work, 0, sizeof(int), st));
-    const int grid = (S_.Nj + C::W - 1) / C::W;
+    const int grid = (S_.ja1 - S_.ja0 + C::W - 1) / C::W;
     k_gs_rows<B, WW, SS><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, g_work, g_err, skip);
     DGB_LAUNCH_OK();
     return 0;
@@ -1018,7 +1027,7 @@ int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double
                    int dir, double omega, const int32_t *skip, cudaStream_t st) {
     int rc = ensure_work(0);
     if (rc) return rc;
-    Stencil S_{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
+    Stencil S_ = make_stencil(Ni, Nj, flags);
     DGB_DISPATCH_B(b, return (gs_rows_launch_t<B>(gs, rhs, x, mbox, S_, dir, omega, skip, st)));
     return 0;
 }
@@ -1049,7 +1058,7 @@ int dgb_check_stencil(const int32_t *indices, const int32_t *indptr, int32_t Ni,
                       int32_t *mismatch, void *stream) {
     DGB_ARG(indices && indptr && mismatch && Ni > 0 && Nj > 0 && flags >= 0);
     cudaStream_t st = (cudaStream_t)stream;
-    Stencil S_{Ni, Nj, (flags & DGB_FLAG_PERIODIC_I) ? 1 : 0, (flags & DGB_FLAG_PERIODIC_J) ? 1 : 0};
+    Stencil S_ = make_stencil(Ni, Nj, flags);
     DGB_CUDA_OK(cudaMemsetAsync(mismatch, 0, sizeof(int32_t), st));
     int g = (Ni * Nj + 255) / 256;
     if (g > sm_count() * 8) g = sm_count() * 8;

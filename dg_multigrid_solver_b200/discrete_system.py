@@ -33,6 +33,10 @@ def stencil_flags(grid, settings):
         f |= _lib.FLAG_PERIODIC_J                       # discrete_system.py:106,117
     if settings.problem.multiply_inverse_mass_matrix:
         f |= _lib.FLAG_MINV                             # discrete_system.py:139
+    if getattr(grid, "ghost_lo", 0):
+        f |= _lib.FLAG_GHOST_LO                         # slab partitioning (parallel.py)
+    if getattr(grid, "ghost_hi", 0):
+        f |= _lib.FLAG_GHOST_HI
     return f
 
 
@@ -73,7 +77,7 @@ class Poisson:
         grid.flags = flags
         grid.nnzb = nnzb
         grid._BSR = None
-        grid.stencil = flags & (_lib.FLAG_PERIODIC_I | _lib.FLAG_PERIODIC_J)   # structure is ours by construction
+        grid.stencil = flags & ~_lib.FLAG_MINV                                 # structure is ours by construction
         prepare_smoother_data(grid)
 
     def assemble_RHS_Poisson(self, grid):

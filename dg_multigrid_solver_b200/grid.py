@@ -46,6 +46,9 @@ class Geometry:
         self.O_grid = settings.grid.O_grid
         self.fully_periodic_boundaries = settings.grid.fully_periodic_boundaries
         self._dev = None
+        # element-slab partitioning (parallel.py): fine element rows of halo available below / above this
+        # slab's own rows inside the local node arrays (0 on a physical boundary or without partitioning)
+        self.halo_lo = self.halo_hi = 0
         if nodes is not None:
             self._from_nodes(*nodes)
         else:
@@ -141,6 +144,14 @@ class Grid:
             setattr(self, k, getattr(geometry, k))
         self.coarsening_factor = None
         self._node_stride = 1
+        # slab partitioning: one ghost element row below / above (the neighbour slab's edge row at this
+        # level's resolution); the level's node window starts `_node_row0` fine element rows into the
+        # local node arrays
+        self.ghost_lo = 1 if geometry.halo_lo > 0 else 0
+        self.ghost_hi = 1 if geometry.halo_hi > 0 else 0
+        self._node_row0 = geometry.halo_lo - self.ghost_lo
+        self.Nj = geometry.Nj - geometry.halo_lo - geometry.halo_hi + self.ghost_lo + self.ghost_hi
+        self.N = self.Ni * self.Nj
         self.vars = vars
         self.discretization = discretization
         self.tables = None
@@ -258,6 +269,8 @@ class Grid:
         torch = _lib.require_cuda()
         T = self.tables
         xn, yn = self.geometry.device_nodes()
+        if self._node_row0:
+            xn, yn = xn[self._node_row0 * self.P_grid:], yn[self._node_row0 * self.P_grid:]
         N = self.Ni * self.Nj
         self.d_vol = torch.empty((N, 7, T.nq), dtype=torch.float64, device="cuda")
         self.d_face = torch.empty((N, 4, 8, T.nq1), dtype=torch.float64, device="cuda")
@@ -306,7 +319,15 @@ class CoarseGrid(Grid):
         self.coarsening_factor = coarsening_factor
         self._node_stride = coarsening_factor
         self.Ni_fine, self.Nj_fine = f.Ni, f.Nj
-        self.Ni, self.Nj = f.Ni // coarsening_factor, f.Nj // coarsening_factor
+        own_rows = f.Nj - f.ghost_lo - f.ghost_hi                      # active fine rows of this slab
+        if own_rows % coarsening_factor != 0:
+            raise ValueError(f"a slab of {own_rows} element rows cannot be coarsened by {coarsening_factor}")
+        g = self.geometry
+        if (self.ghost_lo and g.halo_lo < coarsening_factor) or (self.ghost_hi and g.halo_hi < coarsening_factor):
+            raise ValueError("slab halo too thin for this coarsening factor")
+        self._node_row0 = g.halo_lo - coarsening_factor * self.ghost_lo
+        self.Ni = f.Ni // coarsening_factor
+        self.Nj = own_rows // coarsening_factor + self.ghost_lo + self.ghost_hi
         self.N = self.Ni * self.Nj
         if self.Ni == 0 or self.Nj == 0:
             raise ValueError(f"The number of original elements (Ni,Nj)={(f.Ni, f.Nj)} cannot be divided by a factor {coarsening_factor}")

@@ -82,6 +82,11 @@ typedef struct dgb_operator {
 #define DGB_FLAG_PERIODIC_I 1
 #define DGB_FLAG_PERIODIC_J 2
 #define DGB_FLAG_MINV 4
+/* element-slab partitioning (one slab of whole j-rows per GPU): the local Ni x Nj grid carries one
+ * ghost element row below / above (the neighbour slab's edge row).  Ghost rows have vector entries
+ * (the halo) but no matrix rows; every kernel leaves them untouched. */
+#define DGB_FLAG_GHOST_LO 8
+#define DGB_FLAG_GHOST_HI 16
 
 /* 0 = auto (streaming kernels where the operator allows), 1 = generic kernels only.
  * Returns the previous setting. */
@@ -138,6 +143,12 @@ int dgb_check_stencil(const int32_t *indices, const int32_t *indptr, int32_t Ni,
 int dgb_block_gs_pass(const dgb_operator *h_op, const double *rhs, double *x, int32_t direction,
                       int32_t mode, const int32_t *skip, void *stream);
 
+/* One colour class of the 2-colour sweep: rows with ((i + j + shift) & 1) == colour are relaxed in place.
+ * `shift` carries the global row parity of a slab so that all ranks colour the global grid alike; the
+ * caller exchanges halos between the two colours. */
+int dgb_block_gs_colour(const dgb_operator *h_op, const double *rhs, double *x, int32_t colour, int32_t shift,
+                        const int32_t *skip, void *stream);
+
 /* ---- K8: one block-row relaxation sweep, x_out_i = omega*Dinv_i(rhs_i - sum_{j!=i} A_ij x_in_j)
  *                                                   + (1-omega) x_in_i
  * x_out != x_in : block-Jacobi            (first iteration of dgfem/relaxation.py:123-150)
@@ -176,6 +187,19 @@ int dgb_restrict(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t 
                  int32_t Nj_c, const double *fine, double *coarse, void *stream);
 int dgb_prolong_add(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c,
                     int32_t Nj_c, const double *coarse, double *fine, void *stream);
+
+/* Slab variants (multi-GPU): Nj_c counts the coarse level's local rows INCLUDING its ghost rows
+ * (ghost_c_lo / ghost_c_hi in {0,1}); only active coarse rows are written (restrict) / read (prolong).
+ * For DGB_TRANSFER_H the children of coarse element (I, J) are the fine elements (2I+a_i, 2J+a_j) with
+ * child slot a_j*2+a_i -- what the reference's gather (dgfem/solver.py:164) means on the square global
+ * grid -- and fine local row = ghost_f_lo + 2*(J - ghost_c_lo) + a_j. */
+#define DGB_TRANSFER_H_SLAB 3
+int dgb_restrict_slab(int32_t kind, const double *R, int32_t nc, int32_t nf, int32_t Ni_c, int32_t Nj_c,
+                      int32_t ghost_c_lo, int32_t ghost_c_hi, int32_t ghost_f_lo, const double *fine,
+                      double *coarse, void *stream);
+int dgb_prolong_add_slab(int32_t kind, const double *P, int32_t nc, int32_t nf, int32_t Ni_c, int32_t Nj_c,
+                         int32_t ghost_c_lo, int32_t ghost_c_hi, int32_t ghost_f_lo, const double *coarse,
+                         double *fine, void *stream);
 
 /* ---- V-cycle driver ---------------------------------------------------------------------
  * replaces  Solver.multigrid_V_cycle(k, RHS, u)  (dgfem/solver.py:141-207).

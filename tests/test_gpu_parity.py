@@ -1,5 +1,7 @@
 """GPU tier: the CUDA path (through the C ABI / the reference-facing classes) against the golden
 fixtures generated from the reference, and against the oracle on seeded/synthetic inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -300,3 +302,20 @@ def test_large_grid_properties():
     assert hist[-1] < 1e-6 and len(hist) <= 40
     assert all(h2 < h1 for h1, h2 in zip(hist[:-1], hist[1:]))
     _lib.require_cuda().cuda.synchronize()
+
+
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_slab_partitioned_vcycle(nproc):
+    """DistributedSolver (parallel.py) through torchrun: one rank always (exercises the slab code path
+    with the gathered coarse hierarchy), two ranks when two GPUs are visible."""
+    import subprocess
+    import sys
+    import torch
+    from helpers import REPO
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    port = 29500 + os.getpid() % 2000 + nproc
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "mgpu_check.py"), "64"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "[mgpu_check] PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
