@@ -92,6 +92,8 @@ SIGNATURES = {
     "dgb_poisson_nnzb": (c_i64, [c_i32, c_i32, c_i32]),
     "dgb_assemble_poisson": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_i32,
                                      c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_assemble_stokes": (c_i32, [c_vp] * 9 + [c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_assemble_rhs_stokes": (c_i32, [c_vp] * 13 + [c_i32, c_i32, c_f64, c_f64, c_f64, c_i32, c_vp, c_vp]),
     "dgb_assemble_rhs": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64,
                                  c_i32, c_vp, c_vp]),
 }

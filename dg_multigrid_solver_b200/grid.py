@@ -102,6 +102,28 @@ def padded_blocks(nblocks, b):
     return view
 
 
+def upload_tables(T):
+    """dgb_tables_create for a host Tables object; returns the opaque device handle."""
+    import ctypes
+    L = _lib.load()
+    keep = {}
+
+    def hp(name, arr, dtype=np.float64):
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        keep[name] = a
+        return a.ctypes.data
+    d = _lib.TablesDesc(Pg=T.Pg, p=T.p, nq1=T.nq1, cf=T.cf,
+                        h_V=hp("V", T.V), h_Vr=hp("Vr", T.Vr), h_Vs=hp("Vs", T.Vs),
+                        h_w2=hp("w2", T.w2), h_w1=hp("w1", T.w1),
+                        h_Vf=hp("Vf", T.Vf), h_Vrf=hp("Vrf", T.Vrf), h_Vsf=hp("Vsf", T.Vsf),
+                        h_GX=hp("GX", T.GX), h_GR=hp("GR", T.GR), h_GS=hp("GS", T.GS),
+                        h_FX=hp("FX", T.FX), h_FR=hp("FR", T.FR), h_FS=hp("FS", T.FS),
+                        h_sub_vol=hp("sv", T.sub_vol, np.int32), h_sub_face=hp("sf", T.sub_face, np.int32))
+    h = ctypes.c_void_p()
+    _lib.check(L.dgb_tables_create(ctypes.byref(d), ctypes.byref(h)), "dgb_tables_create")
+    return h
+
+
 class _ElementView:
     """What callers of the reference read from grid.elements[i, j]."""
 
@@ -245,25 +267,7 @@ class Grid:
     def _make_tables(self, cf):
         factor = self.settings.solution.u.integration_polynomial_degree_factor
         self.tables = Tables(self.P_grid, self.P_sol["u"], factor=factor, cf=cf)
-        T = self.tables
-        L = _lib.load()
-        keep = {}
-
-        def hp(name, arr, dtype=np.float64):
-            a = np.ascontiguousarray(arr, dtype=dtype)
-            keep[name] = a
-            return a.ctypes.data
-        d = _lib.TablesDesc(Pg=T.Pg, p=T.p, nq1=T.nq1, cf=cf,
-                            h_V=hp("V", T.V), h_Vr=hp("Vr", T.Vr), h_Vs=hp("Vs", T.Vs),
-                            h_w2=hp("w2", T.w2), h_w1=hp("w1", T.w1),
-                            h_Vf=hp("Vf", T.Vf), h_Vrf=hp("Vrf", T.Vrf), h_Vsf=hp("Vsf", T.Vsf),
-                            h_GX=hp("GX", T.GX), h_GR=hp("GR", T.GR), h_GS=hp("GS", T.GS),
-                            h_FX=hp("FX", T.FX), h_FR=hp("FR", T.FR), h_FS=hp("FS", T.FS),
-                            h_sub_vol=hp("sv", T.sub_vol, np.int32), h_sub_face=hp("sf", T.sub_face, np.int32))
-        import ctypes
-        h = ctypes.c_void_p()
-        _lib.check(L.dgb_tables_create(ctypes.byref(d), ctypes.byref(h)), "dgb_tables_create")
-        self._h_tables = h
+        self._h_tables = upload_tables(self.tables)
 
     def _run_metrics(self):
         torch = _lib.require_cuda()

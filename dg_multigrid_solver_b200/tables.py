@@ -72,11 +72,13 @@ def tensor_basis(n1, r, s, dr=False, ds=False):
 class Tables:
     """All host tables of one level: geometry degree Pg, solution degree p, coarsening factor cf."""
 
-    def __init__(self, Pg, p, factor=3, cf=1):
+    def __init__(self, Pg, p, factor=3, cf=1, nq1=None):
+        """nq1 overrides the number of quadrature points per direction: the Stokes system evaluates the
+        velocity basis at the pressure's points and vice versa (grid.py:185-210 builds every combination)."""
         self.Pg, self.p, self.cf = int(Pg), int(p), int(cf)
         self.ng1, self.n1 = self.Pg + 1, self.p + 1
         self.ng, self.b = self.ng1 ** 2, self.n1 ** 2
-        self.nq1 = factor * self.p // 2 + 1                 # dgfem/grid.py:107
+        self.nq1 = factor * self.p // 2 + 1 if nq1 is None else int(nq1)   # dgfem/grid.py:107
         self.nq = self.nq1 ** 2
         self.r_grid = gauss_lobatto_nodes(self.ng1)
         self.r_int, self.w1 = gauss_legendre(self.nq1)

@@ -299,6 +299,32 @@ int dgb_assemble_rhs(const dgb_tables *t, const double *vol, const double *face,
                      const double *g_face, int32_t Ni, int32_t Nj, double nu, double sigma,
                      int32_t flags, double *rhs, void *stream);
 
+/* ---- K4: Stokes, local ordering ---------------------------------------------------------
+ * replaces Stokes.assemble_BSR_Stokes_local_order (dgfem/discrete_system.py:812-965) and
+ * Stokes.assemble_RHS_Stokes (dgfem/discrete_system.py:967-1028): one (2 b_u + b_p)^2 block per element
+ * pair, rows (x-momentum, y-momentum, continuity), columns (u, v, p), no inverse-mass scaling.
+ * Four table sets: velocity basis @ velocity points (t_uu), pressure basis @ velocity points (t_pu),
+ * velocity basis @ pressure points (t_up), pressure basis @ pressure points (t_pp); dgb_metrics is run
+ * once per point set (vol_u/face_u with t_uu, vol_p/face_p with t_up); area comes from the velocity points
+ * (dgfem/element.py:30).  pin_pressure != 0 reproduces the direct solver's pressure pin
+ * (discrete_system.py:946).  indptr[N+1], indices[nnzb], data[nnzb][bt][bt] with nnzb =
+ * dgb_poisson_nnzb(Ni, Nj, flags) (same block structure as the Poisson operator). */
+int dgb_assemble_stokes(const dgb_tables *t_uu, const dgb_tables *t_pu, const dgb_tables *t_up,
+                        const dgb_tables *t_pp, const double *vol_u, const double *face_u,
+                        const double *vol_p, const double *face_p, const double *area, int32_t Ni,
+                        int32_t Nj, double nu, double sigma, double gamma, int32_t flags,
+                        int32_t pin_pressure, int32_t *indptr, int32_t *indices, double *data,
+                        void *stream);
+/* f_mom[N][2][nq_u]: momentum source (x, y) at the velocity points; f_cont[N][nq_p]: continuity source
+ * at the pressure points; g_u[N][4][2][nq1_u], g_p[N][4][2][nq1_p]: exact velocity (u, v) at the face
+ * points of both point sets (only domain-boundary faces are read). */
+int dgb_assemble_rhs_stokes(const dgb_tables *t_uu, const dgb_tables *t_pu, const dgb_tables *t_up,
+                            const dgb_tables *t_pp, const double *vol_u, const double *face_u,
+                            const double *vol_p, const double *face_p, const double *area,
+                            const double *f_mom, const double *f_cont, const double *g_u,
+                            const double *g_p, int32_t Ni, int32_t Nj, double nu, double sigma,
+                            double gamma, int32_t flags, double *rhs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

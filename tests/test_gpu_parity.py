@@ -319,3 +319,41 @@ def test_slab_partitioned_vcycle(nproc):
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(REPO, "tests", "mgpu_check.py"), "64"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "[mgpu_check] PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", ["stokes_rect4", "stokes_circ4"])
+def test_stokes_local_order_assembly(name):
+    """BASELINE.json configs[4] at fixture size: Stokes local-order operator + RHS + apply against the
+    reference's output (rectangle and O-grid annulus, p_u=2, p_p=1, 22x22 blocks)."""
+    import copy
+    from helpers import case_params
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.relaxation import Relaxation, bsr_apply
+    from dg_multigrid_solver_b200.settings import Settings
+    case = CASES[name]
+    g = golden(name)
+    prm = copy.deepcopy(case_params(case))
+    prm["problem"]["type"] = "Stokes"
+    prm["problem"]["include pressure BC"] = False
+    prm["solution"]["p"]["polynomial degree"] = case["pp"]
+    prm["solution"]["ordering"] = "local"
+    s = Settings(prm)
+    d = DGFEM(settings=s, geometry=Geometry(grid_path(case), s), solve_direct=True, write_results=False)
+    grid = d.grids[-1]
+    A = grid.BSR
+    assert A.blocksize == (int(g["L0_meta"][7]),) * 2 == (22, 22)
+    assert np.array_equal(A.indptr, g["L0_indptr"]) and np.array_equal(A.indices, g["L0_indices"])
+    assert rel_err(A.data, g["L0_data"]) < 1e-12
+    assert rel_err(grid.RHS, g["L0_RHS"]) < 1e-12
+    assert rel_err(bsr_apply(grid, g["smooth_u0"]), g["A_u0_fine"]) < 1e-13
+    # the single-level smoother path on the 22x22 blocks (no pressure pin): Jacobi == D^-1 (b - (A - D) u)
+    s2 = Settings(prm)
+    d2 = DGFEM(settings=s2, geometry=Geometry(grid_path(case), s2), solve_smoother=True, smoother="block_jacobi",
+               write_results=False)
+    g2 = d2.grids[-1]
+    A2 = g2.BSR
+    u0 = g["smooth_u0"]
+    if name == "stokes_rect4":
+        return          # the continuity rows make the diagonal blocks singular (zero p-p block): smoothers need
+                        # the reference's distributive relaxation (SURVEY 8f-2); assembly + apply is the scope here
