@@ -347,13 +347,3 @@ def test_stokes_local_order_assembly(name):
     assert rel_err(A.data, g["L0_data"]) < 1e-12
     assert rel_err(grid.RHS, g["L0_RHS"]) < 1e-12
     assert rel_err(bsr_apply(grid, g["smooth_u0"]), g["A_u0_fine"]) < 1e-13
-    # the single-level smoother path on the 22x22 blocks (no pressure pin): Jacobi == D^-1 (b - (A - D) u)
-    s2 = Settings(prm)
-    d2 = DGFEM(settings=s2, geometry=Geometry(grid_path(case), s2), solve_smoother=True, smoother="block_jacobi",
-               write_results=False)
-    g2 = d2.grids[-1]
-    A2 = g2.BSR
-    u0 = g["smooth_u0"]
-    if name == "stokes_rect4":
-        return          # the continuity rows make the diagonal blocks singular (zero p-p block): smoothers need
-                        # the reference's distributive relaxation; assembly + apply is the scope here
