@@ -30,7 +30,7 @@ class Operator(ctypes.Structure):
     _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
                 ("stencil", c_i32), ("reserved", c_i32),
                 ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp), ("gs_data", c_vp),
-                ("gs_mailbox", c_vp)]
+                ("gs_mailbox", c_vp), ("gs_chain", c_vp)]
 
 
 class Level(ctypes.Structure):
@@ -74,6 +74,8 @@ SIGNATURES = {
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dgb_block_diag_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_gs_chain_len": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
+    "dgb_build_gs_chain": (c_i32, [OP, c_vp]),
     "dgb_check_stencil": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_pass": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_colour": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
@@ -113,7 +115,7 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.dgb_abi_version() != 2:
+    if L.dgb_abi_version() != 3:
         raise DgbError("libdgb200.so ABI version mismatch")
     if os.environ.get("DGB_KERNELS", "auto") == "generic":
         L.dgb_set_kernel_path(1)

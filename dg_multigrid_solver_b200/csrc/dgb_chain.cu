@@ -1,0 +1,535 @@
+// dgb_chain.cu -- lexicographic block Gauss-Seidel, split into a parallel part and a dependency chain.
+//
+// pyamg's block_gauss_seidel (dgfem/pyamg_relaxation.py:252-255) updates the block rows one after the
+// other:  x_e <- Dinv_e (rhs_e - sum_{n != e} A_en x_n), every x_n being the newest value.  On the DG
+// 5-point stencil two of the neighbours of e = (i, j) come EARLIER in the sweep (the previous element of
+// the row and the element of the previous row), the others come LATER and still hold their old values:
+//
+//     x_e  =  c_e  -  M_row(e) x_(i-dir, j)  -  M_up(e) x_(i, j-dir),
+//     c_e  =  Dinv_e (rhs_e - sum_{later n} A_en x_n^old),        M_* = Dinv_e A_e*   (pre-multiplied once)
+//
+//   k_gs_helper  computes every c_e -- no dependencies, a plain streaming kernel over 3 of the 5 blocks;
+//   k_gs_chain   walks the dependency chain.  All it reads is one sequential record stream per element row
+//                ({-M_row, -M_up, c}, brought in by TMA bulk copies), all it computes per element are two
+//                b x b mat-vecs whose inputs are in registers: a warp owns R = 32/b consecutive rows,
+//                lane (g, r) owns scalar row r of element row g, row g runs one element behind row g-1, so
+//                both predecessor values are one warp shuffle away.  Bands of R rows hand their last row
+//                over through a shared-memory ring (same CTA) or the level's global mailbox (next CTA).
+//
+// The sweep order, and therefore the result up to rounding of the re-associated products, is exactly the
+// reference's.  Periodic grids (O-grid wrap) keep the row-pipelined kernel of dgb_stream.cu.
+#include "dgb_async.cuh"
+#include "dgb_common.cuh"
+
+namespace dgb {
+
+int ensure_work(int n_rows);
+int *work_ptr();
+int *err_ptr();
+extern int g_kernel_path;
+extern int g_gs_variant;
+
+template <int B>
+struct ChainCfg {
+    static constexpr int B2 = B * B;
+    static constexpr int R = 32 / B;                                  // element rows per warp
+    static constexpr int REC = (2 * B2 + B + 1) & ~1;                 // doubles per record, 16-byte multiple
+    static constexpr int CH = B <= 4 ? 4 : B <= 9 ? 2 : 1;            // records per bulk copy
+    static constexpr int NS = B <= 16 ? 4 : 3;                        // bulk-copy stages
+    static constexpr int RING = 16;                                   // columns per hand-over ring
+    static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
+    static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
+    static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
+    static constexpr int WDEF = 4;                                    // warps (bands) per CTA
+    static constexpr int RGN = RING * BP;                             // doubles per ring region
+    static constexpr int SCR = RGN + 64;                              // scratch doubles per warp: dummy store targets (ring offset + lane)
+    __host__ __device__ static constexpr int stage_d(int W) { return W * NS * R * CH * REC; }
+    __host__ __device__ static constexpr size_t o_ring(int W) { return sizeof(double) * stage_d(W); }
+    // regions: warp w owns (w, 0) = incoming ring and (w, 1..R) = its rows; (W, 0) is the CTA's outgoing ring
+    __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * (R + 1) * RGN; }
+    __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * W * SCR; }
+    __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * W * NS; }
+    __host__ __device__ static constexpr size_t smem(int W) { return o_prog(W) + sizeof(int) * (W + 1); }
+};
+
+__device__ __forceinline__ bool chain_sentinel(double v) { return __double2hiint(v) == -1; }
+
+// shared-memory accesses by 32-bit address (ptxas folds the constant offsets into the instruction)
+__device__ __forceinline__ double lds1(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// per-lane state of the chain loop: shared-memory addresses (bytes), kept opaque so that they stay in registers
+struct ChainLane {
+    uint32_t up_b;     // ring of the row above (vector reads)
+    uint32_t own_b;    // this row's ring (vector reads of the previous column)
+    uint32_t up_w;     // up_b + 8 r   : my component of the row above (poll)
+    uint32_t own_w;    // own_b + 8 r  : my component of this row (store)
+    uint32_t out_w;    // last row of the band: the next band's incoming ring + 8 r; other rows: scratch
+    uint32_t sen_w;    // first row of the band: up_w (slot handed back); other rows: scratch
+    uint32_t so, sop;  // byte offset of the current / previous column in a ring
+};
+
+// x = c - M_row x_prev - M_up x_up from shared-memory addresses (records hold the negated products)
+template <int B>
+__device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, uint32_t rc /* my c */, uint32_t pv,
+                                             uint32_t uv) {
+    constexpr int B2 = B * B, BP = ChainCfg<B>::BP;
+    double a0 = lds1(rc), a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (B % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < B; c += 2) {
+            const double2 m0 = lds2(rm + c * 8), m1 = lds2(rm + (B2 + c) * 8);
+            const double2 v0 = lds2(pv + c * 8), v1 = lds2(uv + c * 8);
+            a0 = fma(m0.x, v0.x, a0);
+            a1 = fma(m0.y, v0.y, a1);
+            a2 = fma(m1.x, v1.x, a2);
+            a3 = fma(m1.y, v1.y, a3);
+        }
+    } else {
+        double p[BP], u[BP];
+#pragma unroll
+        for (int c = 0; c < BP; c += 2) {
+            const double2 v0 = lds2(pv + c * 8), v1 = lds2(uv + c * 8);
+            p[c] = v0.x; p[c + 1] = v0.y;
+            u[c] = v1.x; u[c + 1] = v1.y;
+        }
+#pragma unroll
+        for (int c = 0; c < B; ++c) {
+            const double m0 = lds1(rm + c * 8), m1 = lds1(rm + (B2 + c) * 8);
+            if (c & 1) {
+                a1 = fma(m0, p[c], a1);
+                a3 = fma(m1, u[c], a3);
+            } else {
+                a0 = fma(m0, p[c], a0);
+                a2 = fma(m1, u[c], a2);
+            }
+        }
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+template <int B, int W, int DIR>
+__global__ void __launch_bounds__(W * 32)
+k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
+           const int32_t *__restrict__ skip) {
+    using C = ChainCfg<B>;
+    constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP, RGN = C::RGN;
+    constexpr int PCH = C::PCH, PSL = C::PSL;
+    constexpr unsigned FULL = 0xffffffffu;
+    if (skip != nullptr && *skip != 0) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_ticket;
+    double *stages = reinterpret_cast<double *>(smem);
+    double *rings = reinterpret_cast<double *>(smem + C::o_ring(W));
+    double *scratch = reinterpret_cast<double *>(smem + C::o_scr(W));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::o_bar(W));
+    volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::o_prog(W));
+    const double sentinel = __longlong_as_double(-1LL);
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
+    if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
+    // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
+    for (int q = threadIdx.x; q < (W + 1) * (R + 1) * RGN; q += W * 32)
+        rings[q] = ((q / RGN) % (R + 1)) == 0 ? sentinel : 0.0;
+    __syncthreads();
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(w));
+    asm volatile("" : "+r"(lane));
+    const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
+    const int band = s_ticket * W + w;
+    const int sr0 = band * R;                      // first row of the band, in sweep order
+    if (sr0 >= nrows) return;
+    const int Rv = min(R, nrows - sr0);            // rows of this band
+    uint64_t *full = bars + w * NS;
+    if (lane == 0) {
+        for (int s = 0; s < NS; ++s) mbar_init(&full[s], Rv);      // one arrival per row of the band
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncwarp();
+    const int g = lane / B, r = lane - g * B;
+    const bool live = g < Rv;
+    const int gq = live ? g : 0;                   // idle lanes shadow row 0 (they never store)
+    const bool g0 = live && g == 0, lastg = live && g == R - 1;
+    const int j = DIR > 0 ? S_.ja0 + sr0 + gq : S_.ja1 - 1 - sr0 - gq;
+    const int j0 = DIR > 0 ? S_.ja0 + sr0 : S_.ja1 - 1 - sr0;
+    const int T = Ni + Rv - 1;                     // steps: row g handles sweep index t - g at step t
+    const int nchunks = (T + CH - 1) / CH;
+    const int pred = sr0 == 0 ? 0 : (w > 0 ? 1 : 2);                          // 0 none, 1 ring, 2 mailbox
+    const int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : 2);
+    double *wstage = stages + (size_t)w * (NS * R * CH * REC);
+    double *inring = rings + (size_t)(w * (R + 1)) * RGN;                     // region (w, 0)
+    double *outr = rings + (size_t)((w + 1) * (R + 1)) * RGN;                 // region (w + 1, 0)
+
+    // lanes 0..Rv-1: bulk copy of chunk n of "their" row (lane index = row) into stage n % NS
+    const double *myrow = rec + (size_t)(j0 + DIR * min(lane, Rv - 1)) * Ni * REC;
+    auto issue = [&](int n) {
+        const int s = n % NS;
+        const int lo = max(0, n * CH - lane), hi = min(Ni, (n + 1) * CH - lane);
+        const uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) * (REC * 8) : 0u;
+        mbar_expect_tx(&full[s], bytes);
+        if (bytes != 0u) {
+            const int klo = lo - (n * CH - lane), khi = hi - (n * CH - lane);
+            const double *src = myrow + (size_t)(DIR > 0 ? lo : Ni - hi) * REC;
+            double *dst = wstage + ((size_t)(s * R + lane) * CH + (DIR > 0 ? klo : CH - khi)) * REC;
+            bulk_g2s(dst, src, bytes, &full[s]);
+        }
+    };
+    if (lane < Rv)
+        for (int n = 0; n < NS && n < nchunks; ++n) issue(n);
+
+    // ---- mailbox polling (first band of a CTA): PCH columns of the predecessor row per poll ----
+    const size_t mrow = (size_t)(j0 - DIR) * Ni;   // predecessor row of the band
+    double PV[PSL];
+    auto mb_load = [&](int m) {
+#pragma unroll
+        for (int sl = 0; sl < PSL; ++sl) {
+            const int q = lane + 32 * sl;
+            const int col = m * PCH + q / B;
+            PV[sl] = 0.0;
+            if (q < PCH * B && col < Ni) PV[sl] = __ldcg(mbox + (mrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (q % B));
+        }
+    };
+    auto mb_take = [&](int m) -> bool {            // wait for chunk m, move it into the incoming ring
+        for (int spin = 0;; ++spin) {
+            bool mine = true;
+#pragma unroll
+            for (int sl = 0; sl < PSL; ++sl) {
+                const int q = lane + 32 * sl;
+                if (q < PCH * B && m * PCH + q / B < Ni && chain_sentinel(PV[sl])) mine = false;
+            }
+            if (__all_sync(FULL, mine)) break;
+            if (spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
+                if (lane == 0) atomicExch(err, 2);
+                return false;
+            }
+            mb_load(m);
+        }
+#pragma unroll
+        for (int sl = 0; sl < PSL; ++sl) {
+            const int q = lane + 32 * sl;
+            const int col = m * PCH + q / B;
+            if (q < PCH * B && col < Ni) {
+                inring[(col % RING) * BP + (q % B)] = PV[sl];
+                __stcg(mbox + (mrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (q % B), sentinel);
+            }
+        }
+        if ((m + 1) * PCH < Ni) mb_load(m + 1);    // checked one poll later
+        return true;
+    };
+    if (pred == 2) mb_load(0);
+
+    ChainLane L;
+    L.up_b = smem_u32(inring + gq * RGN);          // region (w, g): the row above
+    L.own_b = smem_u32(inring + (gq + 1) * RGN);   // region (w, g + 1)
+    L.up_w = L.up_b + 8 * r;
+    L.own_w = L.own_b + 8 * r;
+    const uint32_t scr = smem_u32(scratch + w * C::SCR + lane);
+    L.out_w = lastg ? smem_u32(outr) + 8 * r : scr;
+    L.sen_w = (gq == 0) ? L.up_w : scr + 256;      // idle lanes shadow row 0: they hand back the same slot
+    L.so = (uint32_t)(((RING - gq) % RING) * BP * 8);          // column idx = -g
+    L.sop = (uint32_t)(((2 * RING - gq - 1) % RING) * BP * 8);
+    asm volatile("" : "+r"(L.up_b), "+r"(L.own_b), "+r"(L.up_w), "+r"(L.own_w));
+    asm volatile("" : "+r"(L.out_w), "+r"(L.sen_w));
+    double *xp = x + ((size_t)j * Ni + (DIR > 0 ? 0 : Ni - 1)) * B + r;       // element idx = 0 of my row
+    const uint32_t lane_rm = (uint32_t)((gq * CH * REC + r * B) * 8);         // my matrix rows within a stage
+    const uint32_t lane_rc = (uint32_t)((gq * CH * REC + 2 * B2 + r) * 8);    // my c within a stage
+    const uint32_t stage0 = smem_u32(wstage);
+    int t = 0;
+    for (int n = 0; n < nchunks; ++n) {
+        const int s = n % NS;
+        if (!mbar_wait(&full[s], (uint32_t)((n / NS) & 1), err)) return;
+        // ---- once per chunk: flow control and the global hand-overs ----
+        if (pred == 1 && lane == 0) s_prog[w] = t;                            // columns < t are consumed
+        if (succ == 1) {
+            int spin = 0;
+            while (s_prog[w + 1] < t + CH - RING) {
+                if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+                    if (lane == 0) atomicExch(err, 2);
+                    return;
+                }
+            }
+        }
+        if (pred != 1 && (t % PCH) == 0 && t < Ni) {
+            if (pred == 2) {
+                if (!mb_take(t / PCH)) return;
+            } else {
+                for (int q = lane; q < PCH * BP; q += 32) inring[((t + q / BP) % RING) * BP + (q % BP)] = 0.0;
+            }
+            __syncwarp();
+        }
+        const uint32_t sb = stage0 + (uint32_t)((s * R * CH + (DIR > 0 ? 0 : CH - 1)) * REC * 8);
+        uint32_t rm = sb + lane_rm, rc = sb + lane_rc;
+        const int t0 = t;
+#pragma unroll 1
+        for (int k = 0; k < CH && t < T; ++k, ++t) {
+            if (t >= R - 1 && t < Ni) {
+                // ---- all rows of the band are inside the grid: no predicates ----
+                double mine = lds1(L.up_w + L.so);
+                if (__any_sync(FULL, chain_sentinel(mine))) {      // the neighbour band has not delivered yet
+                    int spin = 0;
+                    do {
+                        mine = lds1(L.up_w + L.so);
+                        if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+                            if (lane == 0) atomicExch(err, 2);
+                            return;
+                        }
+                    } while (__any_sync(FULL, chain_sentinel(mine)));
+                }
+                const double xnew = chain_eval<B>(rm, rc, L.own_b + L.sop, L.up_b + L.so);
+                sts1(L.sen_w + L.so, sentinel);                    // first row: hand the slot back
+                sts1(L.own_w + L.so, xnew);
+                sts1(L.out_w + L.so, xnew);
+                if (live) *xp = xnew;
+                xp += DIR * B;
+            } else {
+                // ---- pipeline fill / drain: some rows are outside [0, Ni) ----
+                const int idx = t - gq;
+                const bool act = live && idx >= 0 && idx < Ni;
+                const bool poll = g0 && t < Ni;
+                double mine = poll ? lds1(L.up_w + L.so) : 0.0;
+                int spin = 0;
+                while (__any_sync(FULL, poll && chain_sentinel(mine))) {
+                    mine = lds1(L.up_w + L.so);
+                    if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+                        if (lane == 0) atomicExch(err, 2);
+                        return;
+                    }
+                }
+                const double xnew = chain_eval<B>(rm, rc, L.own_b + L.sop, L.up_b + L.so);
+                if (poll) sts1(L.up_w + L.so, sentinel);
+                if (act) {
+                    sts1(L.own_w + L.so, xnew);
+                    if (lastg) sts1(L.out_w + L.so, xnew);
+                    *xp = xnew;
+                    if (idx < Ni - 1) xp += DIR * B;
+                }
+            }
+            __syncwarp();
+            rm += DIR * REC * 8;
+            rc += DIR * REC * 8;
+            L.sop = L.so;
+            L.so += BP * 8;
+            if (L.so == RGN * 8) L.so = 0;
+        }
+        // ---- the CTA's last row: this chunk's columns go to the global mailbox ----
+        if (succ == 2) {
+            const size_t lrow = (size_t)(j0 + DIR * (R - 1)) * Ni;
+            for (int q = lane; q < CH * B; q += 32) {
+                const int col = t0 - (R - 1) + q / B;
+                if (col >= 0 && col < Ni && col <= t - 1 - (R - 1))
+                    __stcg(mbox + (lrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (q % B), outr[(col % RING) * BP + (q % B)]);
+            }
+        }
+        __syncwarp();
+        if (lane < Rv && n + NS < nchunks) {
+            fence_proxy_async();
+            issue(n + NS);
+        }
+    }
+}
+
+// ---- the parallel part: c_e = Dinv_e (rhs_e - sum over the neighbours the chain does not handle) ----
+template <int B>
+struct HelperCfg {
+    static constexpr int EPB = (256 / B) > 0 ? (256 / B) : 1;
+    static constexpr int NT = ((EPB * B + 31) / 32) * 32;
+};
+
+template <int B>
+__global__ void __launch_bounds__(HelperCfg<B>::NT)
+k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
+            const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
+            double *rec, Stencil S_, int dir, const int32_t *__restrict__ skip) {
+    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
+    if (skip != nullptr && *skip != 0) return;
+    __shared__ double s_rsum[EPB * B];
+    const int el = threadIdx.x / B, r = threadIdx.x - el * B;
+    const int Ni = S_.Ni;
+    const int first = S_.ja0 * Ni, count = (S_.ja1 - S_.ja0) * Ni;
+    const int ntiles = (count + EPB - 1) / EPB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int idx = tile * EPB + el;
+        const int e = (el < EPB && idx < count) ? first + idx : -1;
+        if (e >= 0) {
+            const int j = e / Ni, i = e - j * Ni;
+            const int e_row = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;       // handled by the chain
+            const int e_up = S_.active(j - dir) ? e - dir * Ni : -1;               // handled by the chain
+            double acc = 0.0;
+            for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+                const int col = indices[jj];
+                if (col == e || col == e_row || col == e_up) continue;
+                const double *a = data + ((size_t)jj * B + r) * B;
+                const double *xv = x + (size_t)col * B;
+                double tt = 0.0;
+#pragma unroll
+                for (int c = 0; c < B; ++c) tt = fma(a[c], xv[c], tt);
+                acc += tt;
+            }
+            s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
+        }
+        __syncthreads();
+        if (e >= 0) {
+            const double *d = dinv + ((size_t)e * B + r) * B;
+            double tt = 0.0;
+#pragma unroll
+            for (int c = 0; c < B; ++c) tt = fma(d[c], s_rsum[el * B + c], tt);
+            rec[(size_t)e * REC + 2 * B2 + r] = tt;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- records: rec[dir][e] = { -Dinv_e A_e,row-predecessor | -Dinv_e A_e,previous-row | c | pad } ----
+template <int B>
+__global__ void __launch_bounds__(256)
+k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ indices,
+                 const int32_t *__restrict__ indptr, const double *__restrict__ dinv, Stencil S_, double *rec) {
+    constexpr int B2 = B * B, REC = ChainCfg<B>::REC;
+    const int Ni = S_.Ni;
+    const long long N = (long long)Ni * S_.Nj;
+    const long long total = N * 4 * B2;
+    for (long long tt = (long long)blockIdx.x * 256 + threadIdx.x; tt < total; tt += (long long)gridDim.x * 256) {
+        const int e = (int)(tt / (4 * B2));
+        const int q = (int)(tt - (long long)e * (4 * B2));
+        const int slot = q / B2, rc = q - slot * B2;
+        const int r = rc / B, c = rc - r * B;
+        const int j = e / Ni, i = e - j * Ni;
+        const int dir = slot < 2 ? 1 : -1;
+        int col = -1;
+        if (S_.active(j)) {
+            if ((slot & 1) == 0) col = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;
+            else col = S_.active(j - dir) ? e - dir * Ni : -1;
+        }
+        double v = 0.0;
+        if (col >= 0) {
+            for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+                if (indices[jj] != col) continue;
+                const double *d = dinv + ((size_t)e * B + r) * B;
+                const double *a = data + (size_t)jj * B2 + c;
+                double s = 0.0;
+                for (int k = 0; k < B; ++k) s = fma(d[k], a[k * B], s);
+                v -= s;
+            }
+        }
+        rec[((size_t)(slot >> 1) * N + e) * REC + (slot & 1) * B2 + rc] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+bool chain_supported(int b, int flags) {
+    if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
+    return flags >= 0 && (flags & 3) == 0 && (b == 4 || b == 9 || b == 16 || b == 25);
+}
+static int chain_rec(int b) {
+    switch (b) {
+    case 4: return ChainCfg<4>::REC;
+    case 9: return ChainCfg<9>::REC;
+    case 16: return ChainCfg<16>::REC;
+    case 25: return ChainCfg<25>::REC;
+    }
+    return 0;
+}
+
+template <int B, int W>
+static int chain_launch_w(const double *rec, double *x, double *mbox, Stencil S_, int dir, const int32_t *skip,
+                          cudaStream_t st) {
+    using C = ChainCfg<B>;
+    static bool configured = false;
+    if (!configured) {
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_chain<B, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::smem(W)));
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_chain<B, W, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::smem(W)));
+        configured = true;
+    }
+    DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
+    const int nbands = (S_.ja1 - S_.ja0 + C::R - 1) / C::R;
+    const int grid = (nbands + W - 1) / W;
+    if (dir > 0)
+        k_gs_chain<B, W, 1><<<grid, W * 32, C::smem(W), st>>>(rec, x, mbox, S_, work_ptr(), err_ptr(), skip);
+    else
+        k_gs_chain<B, W, -1><<<grid, W * 32, C::smem(W), st>>>(rec, x, mbox, S_, work_ptr(), err_ptr(), skip);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+template <int B>
+static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
+                        cudaStream_t st) {
+    using C = ChainCfg<B>;
+    using H = HelperCfg<B>;
+    const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
+    const size_t N = (size_t)op->Ni * op->Nj;
+    double *rec = op->gs_chain + (dir > 0 ? 0 : N * C::REC);
+    const int count = (S_.ja1 - S_.ja0) * S_.Ni;
+    int grid = (count + H::EPB - 1) / H::EPB;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
+        k_gs_helper<B><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, S_, dir, skip);
+        DGB_LAUNCH_OK();
+    }
+    if (g_gs_variant == 21) return 0;
+    if (B <= 9) {
+        if (g_gs_variant == 11) return chain_launch_w<B, 2>(rec, x, op->gs_mailbox, S_, dir, skip, st);
+        if (g_gs_variant == 12) return chain_launch_w<B, 6>(rec, x, op->gs_mailbox, S_, dir, skip, st);
+    }
+    return chain_launch_w<B, C::WDEF>(rec, x, op->gs_mailbox, S_, dir, skip, st);
+}
+
+int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
+                  cudaStream_t st) {
+    int rc = ensure_work(0);
+    if (rc) return rc;
+    switch (op->b) {
+    case 4: return chain_pass_t<4>(op, rhs, x, dir, skip, st);
+    case 9: return chain_pass_t<9>(op, rhs, x, dir, skip, st);
+    case 16: return chain_pass_t<16>(op, rhs, x, dir, skip, st);
+    case 25: return chain_pass_t<25>(op, rhs, x, dir, skip, st);
+    }
+    set_error("gs_chain_pass: unsupported block size b=%d", op->b);
+    return 2;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+
+int64_t dgb_gs_chain_len(int32_t b, int32_t Ni, int32_t Nj, int32_t stencil) {
+    if (!chain_supported(b, stencil) || Ni <= 0 || Nj <= 0) return 0;
+    return 2 * (int64_t)Ni * Nj * chain_rec(b) + 2;
+}
+
+int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
+    DGB_ARG(op != nullptr && op->data && op->indices && op->indptr && op->dinv && op->gs_chain);
+    DGB_ARG(chain_supported(op->b, op->stencil));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
+    const long long N = (long long)op->Ni * op->Nj;
+    DGB_CUDA_OK(cudaMemsetAsync(op->gs_chain, 0, sizeof(double) * (size_t)dgb_gs_chain_len(op->b, op->Ni, op->Nj, op->stencil), st));
+    long long g = (N * 4 * op->b * op->b + 255) / 256;
+    if (g > sm_count() * 16) g = sm_count() * 16;
+    switch (op->b) {
+    case 4: k_build_gs_chain<4><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    case 9: k_build_gs_chain<9><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    case 16: k_build_gs_chain<16><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    case 25: k_build_gs_chain<25><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    }
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+}  // extern "C"

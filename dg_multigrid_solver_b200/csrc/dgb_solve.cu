@@ -367,6 +367,10 @@ int stream_launch(int mode, int b, const double *data, const int32_t *indices, c
 int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double *mbox, int Ni, int Nj, int flags,
                    int dir, double omega, const int32_t *skip, cudaStream_t st);
 enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
+// chained lexicographic GS (dgb_chain.cu)
+bool chain_supported(int b, int flags);
+int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
+                  cudaStream_t st);
 
 // kernels that need the closed-form DG stencil (k_gs_rows)
 static bool use_stream(const dgb_operator *op) {
@@ -503,6 +507,9 @@ static int wavefront_pass(const dgb_operator *op, const double *rhs, double *x, 
 // exact lexicographic order, either kernel family
 static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
                               const int32_t *skip, cudaStream_t st) {
+    if (use_stream(op) && omega == 1.0 && op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
+        chain_supported(op->b, op->stencil))
+        return gs_chain_pass(op, rhs, x, direction, skip, st);
     if (use_stream(op) && op->gs_data != nullptr && op->gs_mailbox != nullptr)
         return gs_rows_launch(op->b, op->gs_data, rhs, x, op->gs_mailbox, op->Ni, op->Nj, op->stencil, direction,
                               omega, skip, st);

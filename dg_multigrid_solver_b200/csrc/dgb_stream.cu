@@ -939,7 +939,9 @@ static int *g_err = nullptr;       // device-side error flag of the async kernel
 int g_kernel_path = 0;             // 0 auto (streaming kernels where available), 1 generic only
 int g_kstream_min_b = 1000;        // k_stream v1 loses to the row-per-thread kernels for every b measured (profiles/r01_probe10); off by default (tuning: dgb_set_kernel_path(200 + b))
 
-static int ensure_work(int n_rows) {
+int *work_ptr() { return g_work; }
+int *err_ptr() { return g_err; }
+int ensure_work(int n_rows) {
     if (g_err == nullptr) {
         DGB_CUDA_OK(cudaMalloc(&g_err, sizeof(int)));
         DGB_CUDA_OK(cudaMemset(g_err, 0, sizeof(int)));

@@ -5,6 +5,9 @@ fills grid.BSR (lazily materialised scipy view of the device BSR arrays) and gri
 The work is done by dgb_assemble_poisson / dgb_assemble_rhs / dgb_block_diag_inverse
 (include/dgb200.h).
 """
+import ctypes
+import os
+
 import numpy as np
 
 from . import _lib
@@ -115,13 +118,22 @@ def prepare_smoother_data(grid):
         _lib.call("dgb_check_stencil", grid.d_indices, grid.d_indptr, grid.Ni, grid.Nj, grid.stencil, mism, st)
         if int(mism.item()) != 0:
             grid.stencil = -1
+    grid.d_gs = grid.d_mailbox = grid.d_chain = None
     if grid.stencil >= 0:
-        grid.d_gs = padded_blocks(int(grid.d_indices.numel()), b)
-        _lib.call("dgb_build_gs_stream", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_dinv, N, b, grid.d_gs, st)
-        # row hand-over mailbox of the lexicographic GS kernel: all-ones (sentinel NaN) outside a pass
+        # row hand-over mailbox of the lexicographic GS kernels: all-ones (sentinel NaN) outside a pass
         grid.d_mailbox = torch.full((N * b,), -1, dtype=torch.int64, device="cuda").view(torch.float64)
-    else:
-        grid.d_gs = grid.d_mailbox = None
+        # chained kernel (two launches per pass: dependency-free part + chain) where the operator allows it,
+        # else the row-pipelined kernel on a copy of the matrix with inverted diagonal blocks
+        chain_len = int(_lib.load().dgb_gs_chain_len(b, int(grid.Ni), int(grid.Nj), int(grid.stencil)))
+        if chain_len > 0:
+            grid.d_chain = torch.empty(chain_len, dtype=torch.float64, device="cuda")
+            op = grid.operator()
+            _lib.call("dgb_build_gs_chain", op, st)
+        nbytes = int(grid.d_indices.numel()) * b * b * 8
+        if chain_len == 0 or os.environ.get("DGB_GS_STREAM") == "1" or nbytes < (64 << 20):
+            grid.d_gs = padded_blocks(int(grid.d_indices.numel()), b)
+            _lib.call("dgb_build_gs_stream", grid.d_data, grid.d_indices, grid.d_indptr, grid.d_dinv, N, b,
+                      grid.d_gs, st)
     return grid.d_dinv
 
 

@@ -180,7 +180,7 @@ class Grid:
         self._h_tables = None
         self.d_vol = self.d_face = self.d_area = None
         self.d_data = self.d_indices = self.d_indptr = None
-        self.d_minv = self.d_dinv = self.d_rhs = self.d_gs = self.d_mailbox = None
+        self.d_minv = self.d_dinv = self.d_rhs = self.d_gs = self.d_mailbox = self.d_chain = None
         self._BSR = self._RHS = self._area_host = None
         self.stencil = -1          # >= 0 once the BSR structure is verified to be the 5-point DG stencil
         self.BSR_E = self.BSR_D = self.BSR_F = None
@@ -212,7 +212,7 @@ class Grid:
             self.d_data.copy_(torch.from_numpy(data))
             self.d_indices = torch.from_numpy(np.ascontiguousarray(value.indices, dtype=np.int32)).cuda()
             self.d_indptr = torch.from_numpy(np.ascontiguousarray(value.indptr, dtype=np.int32)).cuda()
-            self.d_dinv = self.d_gs = self.d_mailbox = None
+            self.d_dinv = self.d_gs = self.d_mailbox = self.d_chain = None
             self.stencil = -1
 
     def operator(self):
@@ -224,7 +224,8 @@ class Grid:
                              indptr=self.d_indptr.data_ptr(),
                              dinv=self.d_dinv.data_ptr() if self.d_dinv is not None else None,
                              gs_data=self.d_gs.data_ptr() if self.d_gs is not None else None,
-                             gs_mailbox=self.d_mailbox.data_ptr() if self.d_mailbox is not None else None)
+                             gs_mailbox=self.d_mailbox.data_ptr() if self.d_mailbox is not None else None,
+                             gs_chain=self.d_chain.data_ptr() if getattr(self, "d_chain", None) is not None else None)
 
     @property
     def RHS(self):

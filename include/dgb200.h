@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DGB_ABI_VERSION 2
+#define DGB_ABI_VERSION 3
 
 /* ---- status ------------------------------------------------------------------------- */
 int dgb_abi_version(void);
@@ -77,6 +77,8 @@ typedef struct dgb_operator {
     const double *gs_data;   /* [nnzb][b][b] smoother stream, or NULL                      */
     double *gs_mailbox;      /* [N*b] row hand-over scratch of the lexicographic GS kernel:
                                 every 8 bytes 0xFF (all-ones NaN) outside a pass, or NULL   */
+    double *gs_chain;        /* [dgb_gs_chain_len()] record stream of the chained lexicographic GS
+                                kernel (dgb_build_gs_chain), or NULL                        */
 } dgb_operator;
 
 #define DGB_FLAG_PERIODIC_I 1
@@ -123,6 +125,15 @@ int dgb_block_diag_inverse(const double *data, const int32_t *indices, const int
 int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_t *indptr,
                         const double *dinv, int32_t n_brow, int32_t b, double *gs_data,
                         void *stream);
+
+/* Chained lexicographic Gauss-Seidel (non-periodic DG stencil, b in {4, 9, 16, 25}): per sweep direction
+ * one record {-Dinv_e A_e,row-predecessor, -Dinv_e A_e,previous-row, c_e} per element, so that the
+ * dependency chain of pyamg's block_gauss_seidel (dgfem/pyamg_relaxation.py:252-255) only needs two
+ * b x b products per element; everything else (c_e) is computed by a dependency-free kernel first.
+ * dgb_gs_chain_len: doubles to allocate for h_op->gs_chain (0 = not supported for this operator, the
+ * row-pipelined kernel on gs_data is used); dgb_build_gs_chain fills it from data / dinv. */
+int64_t dgb_gs_chain_len(int32_t b, int32_t Ni, int32_t Nj, int32_t stencil);
+int dgb_build_gs_chain(const dgb_operator *h_op, void *stream);
 
 /* *mismatch (device int) = number of block rows whose (indptr, indices) differ from the
  * closed-form 5-point stencil of an Ni x Nj DG grid with the given periodicity flags. */

@@ -347,3 +347,52 @@ def test_stokes_local_order_assembly(name):
     assert rel_err(A.data, g["L0_data"]) < 1e-12
     assert rel_err(grid.RHS, g["L0_RHS"]) < 1e-12
     assert rel_err(bsr_apply(grid, g["smooth_u0"]), g["A_u0_fine"]) < 1e-13
+
+
+@pytest.mark.parametrize("Ni,Nj,P", [
+    (3, 5, 1), (1, 7, 1), (7, 1, 2), (2, 2, 1), (17, 9, 2), (40, 33, 1), (33, 40, 2), (8, 8, 3), (6, 7, 4),
+    (64, 64, 1), (130, 70, 2), (70, 130, 1),
+])
+def test_chained_gauss_seidel_kernel(Ni, Nj, P):
+    """k_gs_helper + k_gs_chain (dgb_chain.cu) on ragged grid shapes -- partial bands, single rows/columns,
+    more bands than one CTA holds (mailbox hand-over) -- against the oracle's restatement of pyamg's
+    block_gauss_seidel and against the anti-diagonal wavefront of the generic kernels."""
+    import torch
+    from dgoracle import native
+    from dg_multigrid_solver_b200 import _lib
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.relaxation import Relaxation
+    x, y = _synthetic("rect", Ni, Nj, P)
+    case = dict(grid="synthetic.xyz", pg=P, pu=P, ogrid=False, circ=False, sigmul=1.0)
+    s = make_settings(case)
+    geo = Geometry(None, s, nodes=(np.ascontiguousarray(x.T), np.ascontiguousarray(y.T)))
+    d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg", write_results=False)
+    grid = d.grids[-1]
+    assert grid.d_chain is not None, "chained kernel not selected"
+    L = _lib.load()
+    A = grid.BSR
+    b = A.blocksize[0]
+    rng = np.random.default_rng(Ni * 1000 + Nj)
+    rhs = rng.standard_normal(A.shape[0])
+    x0 = rng.standard_normal(A.shape[0])
+    Dinv = grid.d_dinv.cpu().numpy()
+    for direction, sweeps in (("forward", [1]), ("backward", [-1]), ("symmetric", [1, -1])):
+        ref = x0.copy()
+        N = Ni * Nj
+        for sw in sweeps:
+            span = (0, N, 1) if sw > 0 else (N - 1, -1, -1)
+            native.block_gauss_seidel(A.indptr, A.indices, A.data, ref, rhs, Dinv, *span, b)
+        got = {}
+        try:
+            for path in (0, 1):
+                L.dgb_set_kernel_path(path)
+                got[path] = Relaxation.block_gauss_seidel_pyamg(grid, rhs, x0, direction, 1, 1)
+        finally:
+            L.dgb_set_kernel_path(0)
+        assert L.dgb_device_error(1) == 0
+        scale = np.abs(ref).max()
+        assert np.abs(got[1] - ref).max() <= 1e-12 * scale
+        assert np.abs(got[0] - ref).max() <= 1e-12 * scale, (direction, np.abs(got[0] - ref).max() / scale)
+    # the mailbox is all-sentinel again after the passes
+    assert bool((grid.d_mailbox.view(torch.int64) == -1).all())
