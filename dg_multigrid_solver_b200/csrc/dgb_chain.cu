@@ -69,17 +69,6 @@ __device__ __forceinline__ void sts1(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// per-lane state of the chain loop: shared-memory addresses (bytes), kept opaque so that they stay in registers
-struct ChainLane {
-    uint32_t up_b;     // ring of the row above (vector reads)
-    uint32_t own_b;    // this row's ring (vector reads of the previous column)
-    uint32_t up_w;     // up_b + 8 r   : my component of the row above (poll)
-    uint32_t own_w;    // own_b + 8 r  : my component of this row (store)
-    uint32_t out_w;    // last row of the band: the next band's incoming ring + 8 r; other rows: scratch
-    uint32_t sen_w;    // first row of the band: up_w (slot handed back); other rows: scratch
-    uint32_t so, sop;  // byte offset of the current / previous column in a ring
-};
-
 // x = c - M_row x_prev - M_up x_up from shared-memory addresses (records hold the negated products)
 template <int B>
 __device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, uint32_t rc /* my c */, uint32_t pv,
@@ -119,6 +108,23 @@ __device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, u
     return (a0 + a1) + (a2 + a3);
 }
 
+// Records are stored in the order a band consumes them: rec[dir][band][t][g][REC], band = (row in sweep
+// order) / R, g = row % R, t = (column in sweep order) + g, t < T = Ni + R - 1.  Unused (t, g) are zero.
+template <int B>
+__host__ __device__ __forceinline__ long long chain_loc(const Stencil &S_, int dir, int i, int j) {
+    constexpr int R = ChainCfg<B>::R;
+    const int sr = dir > 0 ? j - S_.ja0 : S_.ja1 - 1 - j;
+    const int idx = dir > 0 ? i : S_.Ni - 1 - i;
+    const int band = sr / R, g = sr - band * R;
+    return ((long long)band * (S_.Ni + R - 1) + idx + g) * R + g;
+}
+template <int B>
+__host__ __device__ __forceinline__ long long chain_dir_records(const Stencil &S_) {
+    constexpr int R = ChainCfg<B>::R;
+    const long long nbands = (S_.ja1 - S_.ja0 + R - 1) / R;
+    return nbands * (S_.Ni + R - 1) * R;
+}
+
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
@@ -126,6 +132,8 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     using C = ChainCfg<B>;
     constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP, RGN = C::RGN;
     constexpr int PCH = C::PCH, PSL = C::PSL;
+    constexpr uint32_t S = BP * 8;                 // bytes per ring slot
+    constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
     if (skip != nullptr && *skip != 0) return;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -141,6 +149,12 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
     for (int q = threadIdx.x; q < (W + 1) * (R + 1) * RGN; q += W * 32)
         rings[q] = ((q / RGN) % (R + 1)) == 0 ? sentinel : 0.0;
+    if ((threadIdx.x & 31) == 0) {
+        uint64_t *bw = bars + (threadIdx.x >> 5) * NS;
+        for (int s = 0; s < NS; ++s) mbar_init(&bw[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
     __syncthreads();
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(w));
@@ -151,15 +165,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     if (sr0 >= nrows) return;
     const int Rv = min(R, nrows - sr0);            // rows of this band
     uint64_t *full = bars + w * NS;
-    if (lane == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&full[s], Rv);      // one arrival per row of the band
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    __syncwarp();
     const int g = lane / B, r = lane - g * B;
     const bool live = g < Rv;
-    const int gq = live ? g : 0;                   // idle lanes shadow row 0 (they never store)
+    const int gq = live ? g : 0;                   // idle lanes shadow row 0 (same values, never stored to x)
     const bool g0 = live && g == 0, lastg = live && g == R - 1;
     const int j = DIR > 0 ? S_.ja0 + sr0 + gq : S_.ja1 - 1 - sr0 - gq;
     const int j0 = DIR > 0 ? S_.ja0 + sr0 : S_.ja1 - 1 - sr0;
@@ -171,21 +179,16 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     double *inring = rings + (size_t)(w * (R + 1)) * RGN;                     // region (w, 0)
     double *outr = rings + (size_t)((w + 1) * (R + 1)) * RGN;                 // region (w + 1, 0)
 
-    // lanes 0..Rv-1: bulk copy of chunk n of "their" row (lane index = row) into stage n % NS
-    const double *myrow = rec + (size_t)(j0 + DIR * min(lane, Rv - 1)) * Ni * REC;
+    // lane 0: one bulk copy per chunk (the records of CH steps of all R rows are contiguous)
+    const double *bsrc = rec + (size_t)band * (Ni + R - 1) * R * REC;
     auto issue = [&](int n) {
         const int s = n % NS;
-        const int lo = max(0, n * CH - lane), hi = min(Ni, (n + 1) * CH - lane);
-        const uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) * (REC * 8) : 0u;
+        const int steps = min(CH, T - n * CH);
+        const uint32_t bytes = (uint32_t)steps * KS;
         mbar_expect_tx(&full[s], bytes);
-        if (bytes != 0u) {
-            const int klo = lo - (n * CH - lane), khi = hi - (n * CH - lane);
-            const double *src = myrow + (size_t)(DIR > 0 ? lo : Ni - hi) * REC;
-            double *dst = wstage + ((size_t)(s * R + lane) * CH + (DIR > 0 ? klo : CH - khi)) * REC;
-            bulk_g2s(dst, src, bytes, &full[s]);
-        }
+        bulk_g2s(wstage + (size_t)s * (CH * R * REC), bsrc + (size_t)n * (CH * R * REC), bytes, &full[s]);
     };
-    if (lane < Rv)
+    if (lane == 0)
         for (int n = 0; n < NS && n < nchunks; ++n) issue(n);
 
     // ---- mailbox polling (first band of a CTA): PCH columns of the predecessor row per poll ----
@@ -229,110 +232,121 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     };
     if (pred == 2) mb_load(0);
 
-    ChainLane L;
-    L.up_b = smem_u32(inring + gq * RGN);          // region (w, g): the row above
-    L.own_b = smem_u32(inring + (gq + 1) * RGN);   // region (w, g + 1)
-    L.up_w = L.up_b + 8 * r;
-    L.own_w = L.own_b + 8 * r;
-    const uint32_t scr = smem_u32(scratch + w * C::SCR + lane);
-    L.out_w = lastg ? smem_u32(outr) + 8 * r : scr;
-    L.sen_w = (gq == 0) ? L.up_w : scr + 256;      // idle lanes shadow row 0: they hand back the same slot
-    L.so = (uint32_t)(((RING - gq) % RING) * BP * 8);          // column idx = -g
-    L.sop = (uint32_t)(((2 * RING - gq - 1) % RING) * BP * 8);
-    asm volatile("" : "+r"(L.up_b), "+r"(L.own_b), "+r"(L.up_w), "+r"(L.own_w));
-    asm volatile("" : "+r"(L.out_w), "+r"(L.sen_w));
-    double *xp = x + ((size_t)j * Ni + (DIR > 0 ? 0 : Ni - 1)) * B + r;       // element idx = 0 of my row
-    const uint32_t lane_rm = (uint32_t)((gq * CH * REC + r * B) * 8);         // my matrix rows within a stage
-    const uint32_t lane_rc = (uint32_t)((gq * CH * REC + 2 * B2 + r) * 8);    // my c within a stage
-    const uint32_t stage0 = smem_u32(wstage);
-    int t = 0;
+    // ---- per-lane shared-memory addresses (bytes), opaque so that they stay in registers ----
+    // Rings are indexed by the STEP that wrote the slot (slot t % RING), except the incoming ring of the band,
+    // which is indexed by column (= the step at which row 0 of the band reads it).
+    //   row g > 0, step t: the row above wrote its column t - g at step t - 1, this row its column t - g - 1 too
+    uint32_t in_b = smem_u32(inring);                                  // region (w, 0)
+    uint32_t up_b = smem_u32(inring + gq * RGN);                       // region (w, g): the row above
+    uint32_t own_b = smem_u32(inring + (gq + 1) * RGN);                // region (w, g + 1)
+    const uint32_t scr = smem_u32(scratch + w * C::SCR);
+    uint32_t out_w = lastg ? smem_u32(outr) + 8 * r : scr + 8 * lane;  // last row -> next band's incoming ring
+    uint32_t sen_w = (gq == 0) ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
+    uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B) * 8);      // my matrix rows, stage 0 step 0
+    uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
+    asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
+    asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c));
+    const bool first_row = gq == 0;
+    double *xrow = x + (size_t)j * Ni * B + r;
+
+    auto spin_fail = [&](int &spin) -> bool {
+        if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+            if (lane == 0) atomicExch(err, 2);
+            return true;
+        }
+        return false;
+    };
+
     for (int n = 0; n < nchunks; ++n) {
         const int s = n % NS;
+        const int t0 = n * CH;
         if (!mbar_wait(&full[s], (uint32_t)((n / NS) & 1), err)) return;
         // ---- once per chunk: flow control and the global hand-overs ----
-        if (pred == 1 && lane == 0) s_prog[w] = t;                            // columns < t are consumed
+        if (pred == 1 && lane == 0) s_prog[w] = t0;                           // columns < t0 are consumed
         if (succ == 1) {
             int spin = 0;
-            while (s_prog[w + 1] < t + CH - RING) {
-                if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
-                    if (lane == 0) atomicExch(err, 2);
-                    return;
-                }
-            }
+            while (s_prog[w + 1] < t0 + CH - RING)
+                if (spin_fail(spin)) return;
         }
-        if (pred != 1 && (t % PCH) == 0 && t < Ni) {
+        if (pred != 1 && (t0 % PCH) == 0 && t0 < Ni) {
             if (pred == 2) {
-                if (!mb_take(t / PCH)) return;
+                if (!mb_take(t0 / PCH)) return;
             } else {
-                for (int q = lane; q < PCH * BP; q += 32) inring[((t + q / BP) % RING) * BP + (q % BP)] = 0.0;
+                for (int q = lane; q < PCH * BP; q += 32) inring[((t0 + q / BP) % RING) * BP + (q % BP)] = 0.0;
             }
             __syncwarp();
         }
-        const uint32_t sb = stage0 + (uint32_t)((s * R * CH + (DIR > 0 ? 0 : CH - 1)) * REC * 8);
-        uint32_t rm = sb + lane_rm, rc = sb + lane_rc;
-        const int t0 = t;
-#pragma unroll 1
-        for (int k = 0; k < CH && t < T; ++k, ++t) {
-            if (t >= R - 1 && t < Ni) {
-                // ---- all rows of the band are inside the grid: no predicates ----
-                double mine = lds1(L.up_w + L.so);
+        const uint32_t so0 = (uint32_t)(t0 % RING) * S;                       // slot of step t0
+        const uint32_t sop0 = (uint32_t)((t0 + RING - 1) % RING) * S;         // slot of step t0 - 1
+        const uint32_t sm = rec_m + (uint32_t)s * (CH * KS), sc = rec_c + (uint32_t)s * (CH * KS);
+        if (t0 >= R - 1 && t0 + CH <= Ni) {
+            // ---- every row of the band is inside the grid for all CH steps: no predicates, immediates ----
+            const uint32_t ua0 = first_row ? in_b + so0 : up_b + sop0;        // vector of the row above, k = 0
+            const uint32_t ua = first_row ? in_b + so0 : up_b + so0 - S;      // ... k >= 1 (+ k S)
+            const uint32_t pa0 = own_b + sop0, pa = own_b + so0 - S;          // previous column of my row
+            const uint32_t ow = own_b + so0 + 8 * r;
+            const uint32_t sw = sen_w + so0;
+            uint32_t oa = out_w + (uint32_t)((t0 - (R - 1)) % RING) * S;      // column-indexed (consumer's view)
+            const uint32_t oend = out_w + RING * S;
+            double *xp = xrow + (size_t)(DIR > 0 ? t0 - gq : Ni - 1 - (t0 - gq)) * B;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const uint32_t uk = k == 0 ? ua0 : ua + k * S;
+                double mine = lds1(uk + 8 * r);
                 if (__any_sync(FULL, chain_sentinel(mine))) {      // the neighbour band has not delivered yet
                     int spin = 0;
                     do {
-                        mine = lds1(L.up_w + L.so);
-                        if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
-                            if (lane == 0) atomicExch(err, 2);
-                            return;
-                        }
+                        mine = lds1(uk + 8 * r);
+                        if (spin_fail(spin)) return;
                     } while (__any_sync(FULL, chain_sentinel(mine)));
                 }
-                const double xnew = chain_eval<B>(rm, rc, L.own_b + L.sop, L.up_b + L.so);
-                sts1(L.sen_w + L.so, sentinel);                    // first row: hand the slot back
-                sts1(L.own_w + L.so, xnew);
-                sts1(L.out_w + L.so, xnew);
-                if (live) *xp = xnew;
-                xp += DIR * B;
-            } else {
-                // ---- pipeline fill / drain: some rows are outside [0, Ni) ----
+                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, k == 0 ? pa0 : pa + k * S, uk);
+                sts1(sw + k * S, sentinel);
+                sts1(ow + k * S, xnew);
+                sts1(oa, xnew);
+                oa += S;
+                if (oa == oend) oa = out_w;
+                if (live) xp[k * DIR * B] = xnew;
+                __syncwarp();
+            }
+        } else {
+            // ---- pipeline fill / drain: some rows are outside [0, Ni) ----
+#pragma unroll 1
+            for (int k = 0; k < CH && t0 + k < T; ++k) {
+                const int t = t0 + k;
                 const int idx = t - gq;
                 const bool act = live && idx >= 0 && idx < Ni;
                 const bool poll = g0 && t < Ni;
-                double mine = poll ? lds1(L.up_w + L.so) : 0.0;
+                const uint32_t so = (uint32_t)(t % RING) * S, sop = (uint32_t)((t + RING - 1) % RING) * S;
+                const uint32_t uk = first_row ? in_b + so : up_b + sop;
+                double mine = poll ? lds1(uk + 8 * r) : 0.0;
                 int spin = 0;
                 while (__any_sync(FULL, poll && chain_sentinel(mine))) {
-                    mine = lds1(L.up_w + L.so);
-                    if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
-                        if (lane == 0) atomicExch(err, 2);
-                        return;
-                    }
+                    mine = lds1(uk + 8 * r);
+                    if (spin_fail(spin)) return;
                 }
-                const double xnew = chain_eval<B>(rm, rc, L.own_b + L.sop, L.up_b + L.so);
-                if (poll) sts1(L.up_w + L.so, sentinel);
+                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, own_b + sop, uk);
+                if (poll) sts1(uk + 8 * r, sentinel);
                 if (act) {
-                    sts1(L.own_w + L.so, xnew);
-                    if (lastg) sts1(L.out_w + L.so, xnew);
-                    *xp = xnew;
-                    if (idx < Ni - 1) xp += DIR * B;
+                    sts1(own_b + so + 8 * r, xnew);
+                    if (lastg) sts1(out_w + (uint32_t)(idx % RING) * S, xnew);
+                    xrow[(size_t)(DIR > 0 ? idx : Ni - 1 - idx) * B] = xnew;
                 }
+                __syncwarp();
             }
-            __syncwarp();
-            rm += DIR * REC * 8;
-            rc += DIR * REC * 8;
-            L.sop = L.so;
-            L.so += BP * 8;
-            if (L.so == RGN * 8) L.so = 0;
         }
         // ---- the CTA's last row: this chunk's columns go to the global mailbox ----
         if (succ == 2) {
             const size_t lrow = (size_t)(j0 + DIR * (R - 1)) * Ni;
+            const int tend = min(t0 + CH, T);
             for (int q = lane; q < CH * B; q += 32) {
                 const int col = t0 - (R - 1) + q / B;
-                if (col >= 0 && col < Ni && col <= t - 1 - (R - 1))
+                if (col >= 0 && col < Ni && col <= tend - 1 - (R - 1))
                     __stcg(mbox + (lrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (q % B), outr[(col % RING) * BP + (q % B)]);
             }
         }
         __syncwarp();
-        if (lane < Rv && n + NS < nchunks) {
+        if (lane == 0 && n + NS < nchunks) {
             fence_proxy_async();
             issue(n + NS);
         }
@@ -384,13 +398,14 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             double tt = 0.0;
 #pragma unroll
             for (int c = 0; c < B; ++c) tt = fma(d[c], s_rsum[el * B + c], tt);
-            rec[(size_t)e * REC + 2 * B2 + r] = tt;
+            const int j = e / Ni, i = e - j * Ni;
+            rec[(size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r] = tt;
         }
         __syncthreads();
     }
 }
 
-// ---- records: rec[dir][e] = { -Dinv_e A_e,row-predecessor | -Dinv_e A_e,previous-row | c | pad } ----
+// ---- records: { -Dinv_e A_e,row-predecessor | -Dinv_e A_e,previous-row | c | pad } at chain_loc(e) ----
 template <int B>
 __global__ void __launch_bounds__(256)
 k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ indices,
@@ -422,7 +437,8 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
                 v -= s;
             }
         }
-        rec[((size_t)(slot >> 1) * N + e) * REC + (slot & 1) * B2 + rc] = v;
+        if (S_.active(j))
+            rec[((size_t)(slot >> 1) * chain_dir_records<B>(S_) + (size_t)chain_loc<B>(S_, dir, i, j)) * REC + (slot & 1) * B2 + rc] = v;
     }
 }
 
@@ -432,12 +448,13 @@ bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     return flags >= 0 && (flags & 3) == 0 && (b == 4 || b == 9 || b == 16 || b == 25);
 }
-static int chain_rec(int b) {
+// doubles of one direction's record stream
+static long long chain_dir_len(int b, const Stencil &S_) {
     switch (b) {
-    case 4: return ChainCfg<4>::REC;
-    case 9: return ChainCfg<9>::REC;
-    case 16: return ChainCfg<16>::REC;
-    case 25: return ChainCfg<25>::REC;
+    case 4: return chain_dir_records<4>(S_) * ChainCfg<4>::REC;
+    case 9: return chain_dir_records<9>(S_) * ChainCfg<9>::REC;
+    case 16: return chain_dir_records<16>(S_) * ChainCfg<16>::REC;
+    case 25: return chain_dir_records<25>(S_) * ChainCfg<25>::REC;
     }
     return 0;
 }
@@ -472,7 +489,7 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
     using H = HelperCfg<B>;
     const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
     const size_t N = (size_t)op->Ni * op->Nj;
-    double *rec = op->gs_chain + (dir > 0 ? 0 : N * C::REC);
+    double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
     if (grid > sm_count() * 8) grid = sm_count() * 8;
@@ -510,7 +527,7 @@ extern "C" {
 
 int64_t dgb_gs_chain_len(int32_t b, int32_t Ni, int32_t Nj, int32_t stencil) {
     if (!chain_supported(b, stencil) || Ni <= 0 || Nj <= 0) return 0;
-    return 2 * (int64_t)Ni * Nj * chain_rec(b) + 2;
+    return 2 * (int64_t)chain_dir_len(b, make_stencil(Ni, Nj, stencil)) + 2;
 }
 
 int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
