@@ -119,6 +119,8 @@ def load(path=None):
         raise DgbError("libdgb200.so ABI version mismatch")
     if os.environ.get("DGB_KERNELS", "auto") == "generic":
         L.dgb_set_kernel_path(1)
+    if os.environ.get("DGB_CHAIN_MASK"):        # tuning: block sizes of the chained Gauss-Seidel kernel
+        L.dgb_set_kernel_path(300 + int(os.environ["DGB_CHAIN_MASK"]))
     _lib = L
     return L
 

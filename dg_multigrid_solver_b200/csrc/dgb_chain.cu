@@ -444,9 +444,13 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
 
 // ---------------------------------------------------------------------------------------
 // host side
+// block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25
+// (dgb_set_kernel_path(300 + mask); the default follows the measurements in profiles/)
+int g_chain_mask = 1;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
-    return flags >= 0 && (flags & 3) == 0 && (b == 4 || b == 9 || b == 16 || b == 25);
+    const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : 0;
+    return flags >= 0 && (flags & 3) == 0 && (g_chain_mask & bit) != 0;
 }
 // doubles of one direction's record stream
 static long long chain_dir_len(int b, const Stencil &S_) {

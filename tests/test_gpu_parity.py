@@ -367,10 +367,25 @@ def test_chained_gauss_seidel_kernel(Ni, Nj, P):
     case = dict(grid="synthetic.xyz", pg=P, pu=P, ogrid=False, circ=False, sigmul=1.0)
     s = make_settings(case)
     geo = Geometry(None, s, nodes=(np.ascontiguousarray(x.T), np.ascontiguousarray(y.T)))
-    d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg", write_results=False)
-    grid = d.grids[-1]
-    assert grid.d_chain is not None, "chained kernel not selected"
     L = _lib.load()
+    L.dgb_set_kernel_path(300 + 15)         # chained kernel for every block size it supports
+    try:
+        d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg",
+                  write_results=False)
+        grid = d.grids[-1]
+        assert grid.d_chain is not None, "chained kernel not selected"
+        _chained_gs_checks(grid, Ni, Nj, L)
+    finally:
+        L.dgb_set_kernel_path(300 + CHAIN_MASK_DEFAULT)
+
+
+CHAIN_MASK_DEFAULT = 1
+
+
+def _chained_gs_checks(grid, Ni, Nj, L):
+    import torch
+    from dgoracle import native
+    from dg_multigrid_solver_b200.relaxation import Relaxation
     A = grid.BSR
     b = A.blocksize[0]
     rng = np.random.default_rng(Ni * 1000 + Nj)
