@@ -34,19 +34,20 @@ struct ChainCfg {
     static constexpr int B2 = B * B;
     static constexpr int R = 32 / B;                                  // element rows per warp
     static constexpr int REC = (2 * B2 + B + 1) & ~1;                 // doubles per record, 16-byte multiple
-    static constexpr int CH = B <= 4 ? 4 : B <= 9 ? 2 : 1;            // records per bulk copy
-    static constexpr int NS = B <= 16 ? 4 : 3;                        // bulk-copy stages
-    static constexpr int RING = 16;                                   // columns per hand-over ring
+    static constexpr int CH = B <= 4 ? 8 : B <= 9 ? 4 : B <= 16 ? 2 : 1;   // steps per chunk (one bulk copy)
+    static constexpr int NS = 3;                                      // bulk-copy stages
+    static constexpr int RING = B <= 4 ? 32 : 16;                     // columns per band hand-over ring
+    static constexpr int RINGR = CH < 2 ? 2 : CH;                     // steps per row ring (rows of one warp)
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
-    static constexpr int WDEF = 4;                                    // warps (bands) per CTA
-    static constexpr int RGN = RING * BP;                             // doubles per ring region
-    static constexpr int SCR = RGN + 64;                              // scratch doubles per warp: dummy store targets (ring offset + lane)
+    static constexpr int WDEF = B <= 4 ? 3 : 4;                       // warps (bands) per CTA
+    static constexpr int WR = (RING + R * RINGR) * BP;                // ring doubles per warp: incoming + rows
+    static constexpr int SCR = RING * BP + 64;                        // scratch doubles per warp: dummy store targets
     __host__ __device__ static constexpr int stage_d(int W) { return W * NS * R * CH * REC; }
     __host__ __device__ static constexpr size_t o_ring(int W) { return sizeof(double) * stage_d(W); }
-    // regions: warp w owns (w, 0) = incoming ring and (w, 1..R) = its rows; (W, 0) is the CTA's outgoing ring
-    __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * (R + 1) * RGN; }
+    // warp w: incoming ring at w * WR, then its R row rings; the CTA's outgoing ring is "warp W"'s incoming ring
+    __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * WR; }
     __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * W * SCR; }
     __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * W * NS; }
     __host__ __device__ static constexpr size_t smem(int W) { return o_prog(W) + sizeof(int) * (W + 1); }
@@ -69,30 +70,40 @@ __device__ __forceinline__ void sts1(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// x = c - M_row x_prev - M_up x_up from shared-memory addresses (records hold the negated products)
+// one ring slot (BP doubles) into registers; *any_sentinel: some entry is the all-ones "not delivered" mark
 template <int B>
-__device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, uint32_t rc /* my c */, uint32_t pv,
-                                             uint32_t uv) {
-    constexpr int B2 = B * B, BP = ChainCfg<B>::BP;
+__device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<B>::BP], bool *any_sentinel) {
+    constexpr int BP = ChainCfg<B>::BP;
+#pragma unroll
+    for (int c = 0; c < BP; c += 2) {
+        const double2 t = lds2(a + c * 8);
+        v[c] = t.x;
+        v[c + 1] = t.y;
+    }
+    if (any_sentinel != nullptr) {
+        unsigned mx = 0u;
+#pragma unroll
+        for (int c = 0; c < B; ++c) mx = max(mx, (unsigned)__double2hiint(v[c]));
+        *any_sentinel = mx == 0xffffffffu;
+    }
+}
+
+// x = c - M_row x_prev - M_up x_up   (records hold the negated products)
+template <int B>
+__device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, uint32_t rc /* my c */,
+                                             const double (&p)[ChainCfg<B>::BP], const double (&u)[ChainCfg<B>::BP]) {
+    constexpr int B2 = B * B;
     double a0 = lds1(rc), a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (B % 2 == 0) {
 #pragma unroll
         for (int c = 0; c < B; c += 2) {
             const double2 m0 = lds2(rm + c * 8), m1 = lds2(rm + (B2 + c) * 8);
-            const double2 v0 = lds2(pv + c * 8), v1 = lds2(uv + c * 8);
-            a0 = fma(m0.x, v0.x, a0);
-            a1 = fma(m0.y, v0.y, a1);
-            a2 = fma(m1.x, v1.x, a2);
-            a3 = fma(m1.y, v1.y, a3);
+            a0 = fma(m0.x, p[c], a0);
+            a1 = fma(m0.y, p[c + 1], a1);
+            a2 = fma(m1.x, u[c], a2);
+            a3 = fma(m1.y, u[c + 1], a3);
         }
     } else {
-        double p[BP], u[BP];
-#pragma unroll
-        for (int c = 0; c < BP; c += 2) {
-            const double2 v0 = lds2(pv + c * 8), v1 = lds2(uv + c * 8);
-            p[c] = v0.x; p[c + 1] = v0.y;
-            u[c] = v1.x; u[c + 1] = v1.y;
-        }
 #pragma unroll
         for (int c = 0; c < B; ++c) {
             const double m0 = lds1(rm + c * 8), m1 = lds1(rm + (B2 + c) * 8);
@@ -130,8 +141,8 @@ __global__ void __launch_bounds__(W * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
            const int32_t *__restrict__ skip) {
     using C = ChainCfg<B>;
-    constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP, RGN = C::RGN;
-    constexpr int PCH = C::PCH, PSL = C::PSL;
+    constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP;
+    constexpr int RINGR = C::RINGR, WR = C::WR, PCH = C::PCH, PSL = C::PSL;
     constexpr uint32_t S = BP * 8;                 // bytes per ring slot
     constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
@@ -147,8 +158,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     if (threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
     if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
     // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
-    for (int q = threadIdx.x; q < (W + 1) * (R + 1) * RGN; q += W * 32)
-        rings[q] = ((q / RGN) % (R + 1)) == 0 ? sentinel : 0.0;
+    for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
     if ((threadIdx.x & 31) == 0) {
         uint64_t *bw = bars + (threadIdx.x >> 5) * NS;
         for (int s = 0; s < NS; ++s) mbar_init(&bw[s], 1);
@@ -176,8 +186,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     const int pred = sr0 == 0 ? 0 : (w > 0 ? 1 : 2);                          // 0 none, 1 ring, 2 mailbox
     const int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : 2);
     double *wstage = stages + (size_t)w * (NS * R * CH * REC);
-    double *inring = rings + (size_t)(w * (R + 1)) * RGN;                     // region (w, 0)
-    double *outr = rings + (size_t)((w + 1) * (R + 1)) * RGN;                 // region (w + 1, 0)
+    double *inring = rings + (size_t)w * WR;                                  // RING slots, indexed by column
+    double *rowring = inring + RING * BP;                                     // R rings of RINGR slots, by step
+    double *outr = rings + (size_t)(w + 1) * WR;                              // the next band's incoming ring
 
     // lane 0: one bulk copy per chunk (the records of CH steps of all R rows are contiguous)
     const double *bsrc = rec + (size_t)band * (Ni + R - 1) * R * REC;
@@ -233,20 +244,22 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     if (pred == 2) mb_load(0);
 
     // ---- per-lane shared-memory addresses (bytes), opaque so that they stay in registers ----
-    // Rings are indexed by the STEP that wrote the slot (slot t % RING), except the incoming ring of the band,
-    // which is indexed by column (= the step at which row 0 of the band reads it).
-    //   row g > 0, step t: the row above wrote its column t - g at step t - 1, this row its column t - g - 1 too
-    uint32_t in_b = smem_u32(inring);                                  // region (w, 0)
-    uint32_t up_b = smem_u32(inring + gq * RGN);                       // region (w, g): the row above
-    uint32_t own_b = smem_u32(inring + (gq + 1) * RGN);                // region (w, g + 1)
+    // Row rings are indexed by the STEP that wrote the slot: row g > 0 at step t finds the value of the row
+    // above (column t - g) and of its own previous column in the slots of step t - 1.  The incoming ring of
+    // the band is indexed by column = the step at which row 0 reads it.
+    const bool first_row = gq == 0;
+    uint32_t in_b = smem_u32(inring);
+    uint32_t up_b = smem_u32(rowring + (gq > 0 ? gq - 1 : 0) * (RINGR * BP));  // ring of the row above (g > 0)
+    uint32_t own_b = smem_u32(rowring + gq * (RINGR * BP));
     const uint32_t scr = smem_u32(scratch + w * C::SCR);
     uint32_t out_w = lastg ? smem_u32(outr) + 8 * r : scr + 8 * lane;  // last row -> next band's incoming ring
-    uint32_t sen_w = (gq == 0) ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
+    uint32_t sen_w = first_row ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
     uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B) * 8);      // my matrix rows, stage 0 step 0
     uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
+    uint32_t own_w = own_b + 8 * r;
+    const uint32_t first_mask = first_row ? 0xffffffffu : 0u;
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
-    asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c));
-    const bool first_row = gq == 0;
+    asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
 
     auto spin_fail = [&](int &spin) -> bool {
@@ -276,31 +289,48 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
             }
             __syncwarp();
         }
-        const uint32_t so0 = (uint32_t)(t0 % RING) * S;                       // slot of step t0
-        const uint32_t sop0 = (uint32_t)((t0 + RING - 1) % RING) * S;         // slot of step t0 - 1
-        const uint32_t sm = rec_m + (uint32_t)s * (CH * KS), sc = rec_c + (uint32_t)s * (CH * KS);
+        const uint32_t si0 = (uint32_t)(t0 % RING) * S;                       // incoming-ring slot of column t0
+        const uint32_t sr0b = (uint32_t)(t0 % RINGR) * S;                     // row-ring slot of step t0 (0 if RINGR == CH)
+        uint32_t sm = rec_m + (uint32_t)s * (CH * KS), sc = rec_c + (uint32_t)s * (CH * KS);
         if (t0 >= R - 1 && t0 + CH <= Ni) {
             // ---- every row of the band is inside the grid for all CH steps: no predicates, immediates ----
-            const uint32_t ua0 = first_row ? in_b + so0 : up_b + sop0;        // vector of the row above, k = 0
-            const uint32_t ua = first_row ? in_b + so0 : up_b + so0 - S;      // ... k >= 1 (+ k S)
-            const uint32_t pa0 = own_b + sop0, pa = own_b + so0 - S;          // previous column of my row
-            const uint32_t ow = own_b + so0 + 8 * r;
-            const uint32_t sw = sen_w + so0;
+            // vector of the row above: row 0 reads column t0 + k of the incoming ring, row g > 0 the slot of step t0 + k - 1
+            uint32_t ua0, ua, pa0, pa, ow;
+            if (RINGR == CH) {
+                ua0 = first_row ? in_b + si0 : up_b + (RINGR - 1) * S;
+                ua = first_row ? in_b + si0 : up_b - S;
+                pa0 = own_b + (RINGR - 1) * S;
+                pa = own_b - S;
+                ow = own_w;
+            } else {        // CH == 1: two-slot row rings
+                ua0 = first_row ? in_b + si0 : up_b + (S - sr0b);
+                ua = ua0;
+                pa0 = own_b + (S - sr0b);
+                pa = pa0;
+                ow = own_w + sr0b;
+            }
+            uint32_t sw = sen_w + (si0 & first_mask);
             uint32_t oa = out_w + (uint32_t)((t0 - (R - 1)) % RING) * S;      // column-indexed (consumer's view)
             const uint32_t oend = out_w + RING * S;
             double *xp = xrow + (size_t)(DIR > 0 ? t0 - gq : Ni - 1 - (t0 - gq)) * B;
+            asm volatile("" : "+r"(ua0), "+r"(ua), "+r"(pa0), "+r"(pa));
+            asm volatile("" : "+r"(ow), "+r"(sw), "+r"(sm), "+r"(sc));
+            asm volatile("" : "+l"(xp));
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const uint32_t uk = k == 0 ? ua0 : ua + k * S;
-                double mine = lds1(uk + 8 * r);
-                if (__any_sync(FULL, chain_sentinel(mine))) {      // the neighbour band has not delivered yet
+                double u[BP], p[BP];
+                bool bad;
+                chain_load_vec<B>(uk, u, &bad);
+                chain_load_vec<B>(k == 0 ? pa0 : pa + k * S, p, nullptr);
+                if (__any_sync(FULL, bad)) {                       // the neighbour band has not delivered yet
                     int spin = 0;
                     do {
-                        mine = lds1(uk + 8 * r);
+                        chain_load_vec<B>(uk, u, &bad);
                         if (spin_fail(spin)) return;
-                    } while (__any_sync(FULL, chain_sentinel(mine)));
+                    } while (__any_sync(FULL, bad));
                 }
-                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, k == 0 ? pa0 : pa + k * S, uk);
+                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, p, u);
                 sts1(sw + k * S, sentinel);
                 sts1(ow + k * S, xnew);
                 sts1(oa, xnew);
@@ -317,18 +347,21 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
                 const int idx = t - gq;
                 const bool act = live && idx >= 0 && idx < Ni;
                 const bool poll = g0 && t < Ni;
-                const uint32_t so = (uint32_t)(t % RING) * S, sop = (uint32_t)((t + RING - 1) % RING) * S;
-                const uint32_t uk = first_row ? in_b + so : up_b + sop;
-                double mine = poll ? lds1(uk + 8 * r) : 0.0;
+                const uint32_t so = (uint32_t)(t % RINGR) * S, sop = (uint32_t)((t + RINGR - 1) % RINGR) * S;
+                const uint32_t uk = first_row ? in_b + (uint32_t)(t % RING) * S : up_b + sop;
+                double u[BP], p[BP];
+                bool bad;
+                chain_load_vec<B>(uk, u, &bad);
+                chain_load_vec<B>(own_b + sop, p, nullptr);
                 int spin = 0;
-                while (__any_sync(FULL, poll && chain_sentinel(mine))) {
-                    mine = lds1(uk + 8 * r);
+                while (__any_sync(FULL, poll && bad)) {
+                    chain_load_vec<B>(uk, u, &bad);
                     if (spin_fail(spin)) return;
                 }
-                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, own_b + sop, uk);
+                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, p, u);
                 if (poll) sts1(uk + 8 * r, sentinel);
                 if (act) {
-                    sts1(own_b + so + 8 * r, xnew);
+                    sts1(own_w + so, xnew);
                     if (lastg) sts1(out_w + (uint32_t)(idx % RING) * S, xnew);
                     xrow[(size_t)(DIR > 0 ? idx : Ni - 1 - idx) * B] = xnew;
                 }
@@ -504,7 +537,6 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
     if (g_gs_variant == 21) return 0;
     if (B <= 9) {
         if (g_gs_variant == 11) return chain_launch_w<B, 2>(rec, x, op->gs_mailbox, S_, dir, skip, st);
-        if (g_gs_variant == 12) return chain_launch_w<B, 6>(rec, x, op->gs_mailbox, S_, dir, skip, st);
     }
     return chain_launch_w<B, C::WDEF>(rec, x, op->gs_mailbox, S_, dir, skip, st);
 }

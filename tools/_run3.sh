@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "chained" > gpurun_out/pytest_chain.log 2>&1; tail -15 gpurun_out/pytest_chain.log | cut -c1-300
 rm -f gpurun_out/probe13.jsonl
-for cfg in "2048 8 1" "2048 32 1" "2048 64 1" "2048 2048 1" "1024 1024 1" "256 256 1" "64 64 1" "2048 3 2" "2048 12 2" "2048 24 2" "2048 2048 2"; do
-  DGB_GS_VARIANT=22 timeout 300 python tools/probe_kernels.py $cfg 5 stream:gs_fwd >> gpurun_out/probe13.jsonl 2>gpurun_out/probe13.err || echo "fail $cfg"
+for cfg in "2048 8 1" "2048 32 1" "2048 2048 1" "1024 1024 1" "256 256 1" "64 64 1" "2048 3 2" "2048 24 2" "2048 2048 2" "1024 2 3" "1024 1024 3" "512 1 4" "512 512 4"; do
+  DGB_CHAIN_MASK=15 DGB_GS_VARIANT=22 timeout 300 python tools/probe_kernels.py $cfg 5 stream:gs_fwd >> gpurun_out/probe13.jsonl 2>gpurun_out/probe13.err || echo "fail $cfg"
 done
 python - <<'PY'
 import json
