@@ -42,7 +42,9 @@ struct ChainCfg {
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
     static constexpr int WDEF = B <= 4 ? 3 : 4;                       // warps (bands) per CTA
-    static constexpr int WR = (RING + R * RINGR) * BP;                // ring doubles per warp: incoming + rows
+    // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
+    static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
+    static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
     static constexpr int SCR = RING * BP + 64;                        // scratch doubles per warp: dummy store targets
     __host__ __device__ static constexpr int stage_d(int W) { return W * NS * R * CH * REC; }
     __host__ __device__ static constexpr size_t o_ring(int W) { return sizeof(double) * stage_d(W); }
@@ -88,35 +90,47 @@ __device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<
     }
 }
 
-// x = c - M_row x_prev - M_up x_up   (records hold the negated products)
+// my rows of the two (negated) pre-multiplied blocks and my entry of c, from the staged record
 template <int B>
-__device__ __forceinline__ double chain_eval(uint32_t rm /* my matrix rows */, uint32_t rc /* my c */,
-                                             const double (&p)[ChainCfg<B>::BP], const double (&u)[ChainCfg<B>::BP]) {
-    constexpr int B2 = B * B;
-    double a0 = lds1(rc), a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (B % 2 == 0) {
+struct ChainRow {
+    double ml[B], mu[B], c;
+    __device__ __forceinline__ void load(uint32_t rm, uint32_t rc) {
+        constexpr int B2 = B * B;
+        c = lds1(rc);
+        if (B % 2 == 0) {
 #pragma unroll
-        for (int c = 0; c < B; c += 2) {
-            const double2 m0 = lds2(rm + c * 8), m1 = lds2(rm + (B2 + c) * 8);
-            a0 = fma(m0.x, p[c], a0);
-            a1 = fma(m0.y, p[c + 1], a1);
-            a2 = fma(m1.x, u[c], a2);
-            a3 = fma(m1.y, u[c + 1], a3);
-        }
-    } else {
+            for (int k = 0; k < B; k += 2) {
+                const double2 m0 = lds2(rm + k * 8), m1 = lds2(rm + (B2 + k) * 8);
+                ml[k] = m0.x; ml[k + 1 < B ? k + 1 : k] = m0.y;
+                mu[k] = m1.x; mu[k + 1 < B ? k + 1 : k] = m1.y;
+            }
+        } else {
 #pragma unroll
-        for (int c = 0; c < B; ++c) {
-            const double m0 = lds1(rm + c * 8), m1 = lds1(rm + (B2 + c) * 8);
-            if (c & 1) {
-                a1 = fma(m0, p[c], a1);
-                a3 = fma(m1, u[c], a3);
-            } else {
-                a0 = fma(m0, p[c], a0);
-                a2 = fma(m1, u[c], a2);
+            for (int k = 0; k < B; ++k) {
+                ml[k] = lds1(rm + k * 8);
+                mu[k] = lds1(rm + (B2 + k) * 8);
             }
         }
     }
-    return (a0 + a1) + (a2 + a3);
+    // x = c - M_row x_prev - M_up x_up   (records hold the negated products)
+    __device__ __forceinline__ double eval(const double (&p)[ChainCfg<B>::BP], const double (&u)[ChainCfg<B>::BP]) const {
+        double a0 = c, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            if (k & 1) {
+                a1 = fma(ml[k], p[k], a1);
+                a3 = fma(mu[k], u[k], a3);
+            } else {
+                a0 = fma(ml[k], p[k], a0);
+                a2 = fma(mu[k], u[k], a2);
+            }
+        }
+        return (a0 + a1) + (a2 + a3);
+    }
+};
+
+__device__ __forceinline__ void stg1(double *p, double v) {
+    asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // Records are stored in the order a band consumes them: rec[dir][band][t][g][REC], band = (row in sweep
@@ -136,13 +150,36 @@ __host__ __device__ __forceinline__ long long chain_dir_records(const Stencil &S
     return nbands * (S_.Ni + R - 1) * R;
 }
 
+// slow path of a step: spin until the row above has delivered this column (whole warp, uniform)
+template <int B>
+__device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
+    constexpr int BP = ChainCfg<B>::BP;
+    int spin = 0;
+    bool bad;
+    do {
+        unsigned mx = 0u;
+#pragma unroll
+        for (int c = 0; c < BP; c += 2) {
+            const double2 t = lds2(uk + c * 8);
+            mx = max(mx, (unsigned)__double2hiint(t.x));
+            if (c + 1 < B) mx = max(mx, (unsigned)__double2hiint(t.y));
+        }
+        bad = mx == 0xffffffffu;
+        if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+            if ((threadIdx.x & 31) == 0) atomicExch(err, 2);
+            return false;
+        }
+    } while (__any_sync(0xffffffffu, bad));
+    return true;
+}
+
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
            const int32_t *__restrict__ skip) {
     using C = ChainCfg<B>;
     constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP;
-    constexpr int RINGR = C::RINGR, WR = C::WR, PCH = C::PCH, PSL = C::PSL;
+    constexpr int RINGR = C::RINGR, WR = C::WR, RRS = C::RRS, PCH = C::PCH, PSL = C::PSL;
     constexpr uint32_t S = BP * 8;                 // bytes per ring slot
     constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
@@ -183,8 +220,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     const int j0 = DIR > 0 ? S_.ja0 + sr0 : S_.ja1 - 1 - sr0;
     const int T = Ni + Rv - 1;                     // steps: row g handles sweep index t - g at step t
     const int nchunks = (T + CH - 1) / CH;
-    const int pred = sr0 == 0 ? 0 : (w > 0 ? 1 : 2);                          // 0 none, 1 ring, 2 mailbox
-    const int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : 2);
+    int pred = sr0 == 0 ? 0 : (w > 0 ? 1 : 2);                                // 0 none, 1 ring, 2 mailbox
+    int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : 2);
+    asm volatile("" : "+r"(pred), "+r"(succ));
     double *wstage = stages + (size_t)w * (NS * R * CH * REC);
     double *inring = rings + (size_t)w * WR;                                  // RING slots, indexed by column
     double *rowring = inring + RING * BP;                                     // R rings of RINGR slots, by step
@@ -249,8 +287,8 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     // the band is indexed by column = the step at which row 0 reads it.
     const bool first_row = gq == 0;
     uint32_t in_b = smem_u32(inring);
-    uint32_t up_b = smem_u32(rowring + (gq > 0 ? gq - 1 : 0) * (RINGR * BP));  // ring of the row above (g > 0)
-    uint32_t own_b = smem_u32(rowring + gq * (RINGR * BP));
+    uint32_t up_b = smem_u32(rowring + (gq > 0 ? gq - 1 : 0) * RRS);   // ring of the row above (g > 0)
+    uint32_t own_b = smem_u32(rowring + gq * RRS);
     const uint32_t scr = smem_u32(scratch + w * C::SCR);
     uint32_t out_w = lastg ? smem_u32(outr) + 8 * r : scr + 8 * lane;  // last row -> next band's incoming ring
     uint32_t sen_w = first_row ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
@@ -262,7 +300,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
 
-    auto spin_fail = [&](int &spin) -> bool {
+    auto spin_fail = [=](int &spin) -> bool {
         if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
             if (lane == 0) atomicExch(err, 2);
             return true;
@@ -320,23 +358,24 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
             for (int k = 0; k < CH; ++k) {
                 const uint32_t uk = k == 0 ? ua0 : ua + k * S;
                 double u[BP], p[BP];
+                ChainRow<B> row;
                 bool bad;
                 chain_load_vec<B>(uk, u, &bad);
                 chain_load_vec<B>(k == 0 ? pa0 : pa + k * S, p, nullptr);
-                if (__any_sync(FULL, bad)) {                       // the neighbour band has not delivered yet
-                    int spin = 0;
-                    do {
-                        chain_load_vec<B>(uk, u, &bad);
-                        if (spin_fail(spin)) return;
-                    } while (__any_sync(FULL, bad));
+                row.load(sm + k * KS, sc + k * KS);
+                const bool wait_up = __any_sync(FULL, bad);        // the neighbour band has not delivered yet?
+                double xnew = row.eval(p, u);
+                if (__builtin_expect(wait_up, 0)) {
+                    if (!chain_wait_up<B>(uk, err)) return;
+                    chain_load_vec<B>(uk, u, nullptr);
+                    xnew = row.eval(p, u);
                 }
-                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, p, u);
                 sts1(sw + k * S, sentinel);
                 sts1(ow + k * S, xnew);
                 sts1(oa, xnew);
                 oa += S;
                 if (oa == oend) oa = out_w;
-                if (live) xp[k * DIR * B] = xnew;
+                if (live) stg1(xp + k * DIR * B, xnew);
                 __syncwarp();
             }
         } else {
@@ -358,7 +397,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
                     chain_load_vec<B>(uk, u, &bad);
                     if (spin_fail(spin)) return;
                 }
-                const double xnew = chain_eval<B>(sm + k * KS, sc + k * KS, p, u);
+                ChainRow<B> row;
+                row.load(sm + k * KS, sc + k * KS);
+                const double xnew = row.eval(p, u);
                 if (poll) sts1(uk + 8 * r, sentinel);
                 if (act) {
                     sts1(own_w + so, xnew);

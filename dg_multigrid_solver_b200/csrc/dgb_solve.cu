@@ -387,6 +387,46 @@ static int check_op(const dgb_operator *op) {
 }
 }  // namespace dgb
 
+namespace dgb {
+// Relaxation.block_gauss_seidel_pyamg on the device (dgfem/relaxation.py:198-218).  r_keep (optional): every
+// residual test also stores the residual vector, so that after the call r_keep == rhs - A u for the u the
+// smoother returns (the tests after an early exit are no-ops and u no longer changes) -- the V-cycle reuses it
+// for the restriction instead of evaluating the same residual again (dgfem/solver.py:150).
+int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direction, int32_t max_iterations,
+             int32_t mode, int32_t check_residual, dgb_smoother_ctl *ctl, double *partials, double *sumsq,
+             double *r_keep, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(ctl && partials && sumsq);
+    DGB_ARG(direction == 0 || direction == 1 || direction == -1);
+    const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
+    if (check_residual) {
+        rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, nullptr, stream);
+        if (rc) return rc;
+        rc = dgb_smoother_begin(ctl, sumsq, n, stream);
+        if (rc) return rc;
+    }
+    const int32_t *skip = check_residual ? &ctl->skip : nullptr;
+    for (int it = 0; it < max_iterations; ++it) {
+        if (direction >= 0) {
+            rc = dgb_block_gs_pass(op, rhs, u, +1, mode, skip, stream);
+            if (rc) return rc;
+        }
+        if (direction <= 0) {
+            rc = dgb_block_gs_pass(op, rhs, u, -1, mode, skip, stream);
+            if (rc) return rc;
+        }
+        if (check_residual) {
+            rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, skip, stream);
+            if (rc) return rc;
+            rc = dgb_smoother_check(ctl, sumsq, n, stream);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+}  // namespace dgb
+
 using namespace dgb;
 
 // =========================================================================================
@@ -582,35 +622,8 @@ int dgb_block_gauss_seidel_pyamg(const dgb_operator *op, const double *rhs, doub
                                  int32_t direction, int32_t max_iterations, int32_t mode,
                                  int32_t check_residual, dgb_smoother_ctl *ctl, double *partials,
                                  double *sumsq, void *stream) {
-    int rc = check_op(op);
-    if (rc) return rc;
-    DGB_ARG(ctl && partials && sumsq);
-    DGB_ARG(direction == 0 || direction == 1 || direction == -1);
-    const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
-    if (check_residual) {
-        rc = dgb_bsr_residual(op, rhs, u, nullptr, partials, sumsq, nullptr, stream);
-        if (rc) return rc;
-        rc = dgb_smoother_begin(ctl, sumsq, n, stream);
-        if (rc) return rc;
-    }
-    const int32_t *skip = check_residual ? &ctl->skip : nullptr;
-    for (int it = 0; it < max_iterations; ++it) {
-        if (direction >= 0) {
-            rc = dgb_block_gs_pass(op, rhs, u, +1, mode, skip, stream);
-            if (rc) return rc;
-        }
-        if (direction <= 0) {
-            rc = dgb_block_gs_pass(op, rhs, u, -1, mode, skip, stream);
-            if (rc) return rc;
-        }
-        if (check_residual) {
-            rc = dgb_bsr_residual(op, rhs, u, nullptr, partials, sumsq, skip, stream);
-            if (rc) return rc;
-            rc = dgb_smoother_check(ctl, sumsq, n, stream);
-            if (rc) return rc;
-        }
-    }
-    return 0;
+    return dgb::gs_pyamg(op, rhs, u, direction, max_iterations, mode, check_residual, ctl, partials, sumsq, nullptr,
+                         stream);
 }
 
 static int transfer_launch(bool restrict_dir, int32_t kind, const double *M, int32_t nc, int32_t nf, int32_t Ni_c,

@@ -9,14 +9,20 @@
 
 namespace dgb {
 
+// *have_residual (optional, out): L.r holds rhs - A u of the returned u (the smoother's own last residual test)
 static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream) {
+                  double *partials, double *sumsq, void *stream, bool *have_residual = nullptr) {
+    if (have_residual) *have_residual = false;
     if (iterations <= 0) return 0;
     const size_t nbytes = sizeof(double) * (size_t)L.op.Ni * L.op.Nj * L.op.b;
     switch (L.smoother) {
     case DGB_SMOOTHER_BLOCK_GS_PYAMG:
-        return dgb_block_gauss_seidel_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode,
-                                            o.check_residual, ctl, partials, sumsq, stream);
+        if (have_residual && o.check_residual) {
+            *have_residual = true;
+            return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream);
+        }
+        return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
+                        nullptr, stream);
     case DGB_SMOOTHER_BLOCK_JACOBI: {
         // relaxation.py:123-150: iteration 1 is Jacobi into a fresh buffer, then `u = u_new`
         // aliases the two, so the remaining iterations are in-place forward sweeps.
@@ -47,9 +53,11 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     if (k == 0)   // solver.py:201-204
         return smooth(L, o, o.coarse_iterations, ctl + k, partials, sumsq, stream);
     const dgb_level &C = lv[k - 1];
-    if ((rc = smooth(L, o, L.pre_iterations, ctl + k, partials, sumsq, stream))) return rc;
-    // residual = RHS - BSR @ u (solver.py:150)
-    if ((rc = dgb_bsr_residual(&L.op, L.rhs, L.u, L.r, partials, sumsq, nullptr, stream))) return rc;
+    bool have_r = false;
+    if ((rc = smooth(L, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r))) return rc;
+    // residual = RHS - BSR @ u (solver.py:150); the pre-smoother's last residual test already evaluated exactly
+    // this vector (same kernel, same inputs), so it is not computed twice
+    if (!have_r && (rc = dgb_bsr_residual(&L.op, L.rhs, L.u, L.r, partials, sumsq, nullptr, stream))) return rc;
     if ((rc = dgb_restrict(C.transfer_kind, C.R, C.nc, C.nf, C.op.Ni, C.op.Nj, L.r, C.rhs, stream))) return rc;
     DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.op.Ni * C.op.Nj * C.op.b, st));   // solver.py:171
     if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream))) return rc;
