@@ -8,7 +8,11 @@
 //     x_e  =  c_e  -  M_row(e) x_(i-dir, j)  -  M_up(e) x_(i, j-dir),
 //     c_e  =  Dinv_e (rhs_e - sum_{later n} A_en x_n^old),        M_* = Dinv_e A_e*   (pre-multiplied once)
 //
-//   k_gs_helper  computes every c_e -- no dependencies, a plain streaming kernel over 3 of the 5 blocks;
+//   k_gs_helper  computes every c_e -- no dependencies, a plain streaming kernel over 3 of the 5 blocks.
+//                In a symmetric sweep (forward, backward, forward, ...) only the FIRST pass needs it: the chain
+//                of one direction hands the next pass its c for free, because what it subtracted is exactly
+//                what the opposite direction's c must leave out:
+//                    c_next(e) = Dinv_e rhs_e - (c_e - x_e)        (d_e = Dinv_e rhs_e is kept in the record);
 //   k_gs_chain   walks the dependency chain.  All it reads is one sequential record stream per element row
 //                ({-M_row, -M_up, c}, brought in by TMA bulk copies), all it computes per element are two
 //                b x b mat-vecs whose inputs are in registers: a warp owns R = 32/b consecutive rows,
@@ -33,7 +37,7 @@ template <int B>
 struct ChainCfg {
     static constexpr int B2 = B * B;
     static constexpr int R = 32 / B;                                  // element rows per warp
-    static constexpr int REC = (2 * B2 + B + 1) & ~1;                 // doubles per record, 16-byte multiple
+    static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
     static constexpr int CH = B <= 4 ? 8 : B <= 9 ? 4 : B <= 16 ? 2 : 1;   // steps per chunk (one bulk copy)
     static constexpr int NS = 3;                                      // bulk-copy stages
     static constexpr int RING = B <= 4 ? 32 : 16;                     // columns per band hand-over ring
@@ -41,7 +45,7 @@ struct ChainCfg {
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
-    static constexpr int WDEF = B <= 4 ? 3 : 4;                       // warps (bands) per CTA
+    static constexpr int WDEF = (B <= 4 || B == 16) ? 3 : 4;          // warps (bands) per CTA (shared memory bound)
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
     static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
     static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
@@ -93,10 +97,11 @@ __device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<
 // my rows of the two (negated) pre-multiplied blocks and my entry of c, from the staged record
 template <int B>
 struct ChainRow {
-    double ml[B], mu[B], c;
+    double ml[B], mu[B], c, d;
     __device__ __forceinline__ void load(uint32_t rm, uint32_t rc) {
         constexpr int B2 = B * B;
         c = lds1(rc);
+        d = lds1(rc + B * 8);
         if (B % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < B; k += 2) {
@@ -128,6 +133,38 @@ struct ChainRow {
         return (a0 + a1) + (a2 + a3);
     }
 };
+
+// ---- thread-block cluster primitives (distributed shared memory) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(v) : "r"(local_smem_addr), "r"(rank));
+    return v;
+}
+__device__ __forceinline__ void sts1_cluster(uint32_t a, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_cluster_u32(uint32_t a, int v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ldv_cluster_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ void stg1(double *p, double v) {
     asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -175,8 +212,8 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
 
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
-k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
-           const int32_t *__restrict__ skip) {
+k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, double *__restrict__ x, double *mbox,
+           Stencil S_, int *work, int *err, const int32_t *__restrict__ skip) {
     using C = ChainCfg<B>;
     constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP;
     constexpr int RINGR = C::RINGR, WR = C::WR, RRS = C::RRS, PCH = C::PCH, PSL = C::PSL;
@@ -192,7 +229,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::o_bar(W));
     volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::o_prog(W));
     const double sentinel = __longlong_as_double(-1LL);
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
+    // one ticket per cluster: the CTAs of a cluster take consecutive groups of W bands and hand their last row
+    // over through distributed shared memory; only the last CTA of a cluster uses the global mailbox
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    if (crank == 0 && threadIdx.x == 0) {
+        const int tk = atomicAdd(&work[0], 1);
+        for (uint32_t c = 0; c < csize; ++c) sts_cluster_u32(cluster_map(smem_u32(&s_ticket), c), tk);
+    }
     if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
     // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
     for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
@@ -202,12 +245,12 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
         fence_barrier_init();
         fence_proxy_async();
     }
-    __syncthreads();
+    cluster_sync_all();            // rings initialised and the ticket delivered in every CTA of the cluster
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(w));
     asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
-    const int band = s_ticket * W + w;
+    const int band = (s_ticket * (int)csize + (int)crank) * W + w;
     const int sr0 = band * R;                      // first row of the band, in sweep order
     if (sr0 >= nrows) return;
     const int Rv = min(R, nrows - sr0);            // rows of this band
@@ -220,8 +263,10 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     const int j0 = DIR > 0 ? S_.ja0 + sr0 : S_.ja1 - 1 - sr0;
     const int T = Ni + Rv - 1;                     // steps: row g handles sweep index t - g at step t
     const int nchunks = (T + CH - 1) / CH;
-    int pred = sr0 == 0 ? 0 : (w > 0 ? 1 : 2);                                // 0 none, 1 ring, 2 mailbox
-    int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : 2);
+    // predecessor: 0 none, 1 shared-memory ring (previous warp, or previous CTA of the cluster), 2 global mailbox
+    // successor:   0 none, 1 ring of the next warp, 3 ring of the next CTA of the cluster, 2 global mailbox
+    int pred = sr0 == 0 ? 0 : ((w > 0 || crank > 0) ? 1 : 2);
+    int succ = (band + 1) * R >= nrows ? 0 : (w < W - 1 ? 1 : (crank + 1 < csize ? 3 : 2));
     asm volatile("" : "+r"(pred), "+r"(succ));
     double *wstage = stages + (size_t)w * (NS * R * CH * REC);
     double *inring = rings + (size_t)w * WR;                                  // RING slots, indexed by column
@@ -290,7 +335,11 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     uint32_t up_b = smem_u32(rowring + (gq > 0 ? gq - 1 : 0) * RRS);   // ring of the row above (g > 0)
     uint32_t own_b = smem_u32(rowring + gq * RRS);
     const uint32_t scr = smem_u32(scratch + w * C::SCR);
-    uint32_t out_w = lastg ? smem_u32(outr) + 8 * r : scr + 8 * lane;  // last row -> next band's incoming ring
+    // last row -> next band's incoming ring (shared::cluster address: this CTA's, or warp 0 of the next CTA)
+    uint32_t out_w = lastg ? (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank)) + 8 * r
+                           : cluster_map(scr, crank) + 8 * lane;
+    const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
+                                         : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
     uint32_t sen_w = first_row ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
     uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B) * 8);      // my matrix rows, stage 0 step 0
     uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
@@ -299,6 +348,15 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
     asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
+    // my entry of c in the OTHER direction's record of sweep index idx: a constant stride of -R records per step
+    // (the opposite sweep visits the rows and the columns in reverse order)
+    double *corow;
+    {
+        const int sro = nrows - 1 - (sr0 + gq);                // my row in the opposite sweep order
+        const int bo = sro / R, go = sro - bo * R;
+        corow = rec_other + (((size_t)bo * (Ni + R - 1) + (Ni - 1) + go) * R + go) * REC + 2 * B2 + r;   // idx = 0
+    }
+    constexpr long long COS = -(long long)R * REC;          // doubles per step
 
     auto spin_fail = [=](int &spin) -> bool {
         if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
@@ -314,9 +372,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
         if (!mbar_wait(&full[s], (uint32_t)((n / NS) & 1), err)) return;
         // ---- once per chunk: flow control and the global hand-overs ----
         if (pred == 1 && lane == 0) s_prog[w] = t0;                           // columns < t0 are consumed
-        if (succ == 1) {
+        if (succ == 1 || succ == 3) {
             int spin = 0;
-            while (s_prog[w + 1] < t0 + CH - RING)
+            while (ldv_cluster_s32(prog_next) < t0 + CH - RING)
                 if (spin_fail(spin)) return;
         }
         if (pred != 1 && (t0 % PCH) == 0 && t0 < Ni) {
@@ -351,9 +409,10 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
             uint32_t oa = out_w + (uint32_t)((t0 - (R - 1)) % RING) * S;      // column-indexed (consumer's view)
             const uint32_t oend = out_w + RING * S;
             double *xp = xrow + (size_t)(DIR > 0 ? t0 - gq : Ni - 1 - (t0 - gq)) * B;
+            double *cop = corow + (long long)(t0 - gq) * COS;
             asm volatile("" : "+r"(ua0), "+r"(ua), "+r"(pa0), "+r"(pa));
             asm volatile("" : "+r"(ow), "+r"(sw), "+r"(sm), "+r"(sc));
-            asm volatile("" : "+l"(xp));
+            asm volatile("" : "+l"(xp), "+l"(cop));
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const uint32_t uk = k == 0 ? ua0 : ua + k * S;
@@ -372,10 +431,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
                 }
                 sts1(sw + k * S, sentinel);
                 sts1(ow + k * S, xnew);
-                sts1(oa, xnew);
+                sts1_cluster(oa, xnew);
                 oa += S;
                 if (oa == oend) oa = out_w;
-                if (live) stg1(xp + k * DIR * B, xnew);
+                if (live) {
+                    stg1(xp + k * DIR * B, xnew);
+                    stg1(cop + k * COS, (row.d - row.c) + xnew);       // the next (opposite) pass's c
+                }
                 __syncwarp();
             }
         } else {
@@ -403,8 +465,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ x, double *mbox,
                 if (poll) sts1(uk + 8 * r, sentinel);
                 if (act) {
                     sts1(own_w + so, xnew);
-                    if (lastg) sts1(out_w + (uint32_t)(idx % RING) * S, xnew);
+                    if (lastg) sts1_cluster(out_w + (uint32_t)(idx % RING) * S, xnew);
                     xrow[(size_t)(DIR > 0 ? idx : Ni - 1 - idx) * B] = xnew;
+                    corow[(long long)idx * COS] = (row.d - row.c) + xnew;
                 }
                 __syncwarp();
             }
@@ -438,10 +501,11 @@ template <int B>
 __global__ void __launch_bounds__(HelperCfg<B>::NT)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
-            double *rec, Stencil S_, int dir, const int32_t *__restrict__ skip) {
+            double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip) {
     constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
     if (skip != nullptr && *skip != 0) return;
     __shared__ double s_rsum[EPB * B];
+    __shared__ double s_rhs[EPB * B];
     const int el = threadIdx.x / B, r = threadIdx.x - el * B;
     const int Ni = S_.Ni;
     const int first = S_.ja0 * Ni, count = (S_.ja1 - S_.ja0) * Ni;
@@ -464,16 +528,24 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
                 for (int c = 0; c < B; ++c) tt = fma(a[c], xv[c], tt);
                 acc += tt;
             }
-            s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
+            const double f = rhs[(size_t)e * B + r];
+            s_rhs[el * B + r] = f;
+            s_rsum[el * B + r] = f - acc;
         }
         __syncthreads();
         if (e >= 0) {
             const double *d = dinv + ((size_t)e * B + r) * B;
-            double tt = 0.0;
+            double tt = 0.0, td = 0.0;
 #pragma unroll
-            for (int c = 0; c < B; ++c) tt = fma(d[c], s_rsum[el * B + c], tt);
+            for (int c = 0; c < B; ++c) {
+                tt = fma(d[c], s_rsum[el * B + c], tt);
+                td = fma(d[c], s_rhs[el * B + c], td);
+            }
             const int j = e / Ni, i = e - j * Ni;
-            rec[(size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r] = tt;
+            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r;
+            mine[0] = tt;                                   // c_e
+            mine[B] = td;                                   // d_e = Dinv_e rhs_e, for both sweep directions
+            rec_other[(size_t)chain_loc<B>(S_, -dir, i, j) * REC + 2 * B2 + B + r] = td;
         }
         __syncthreads();
     }
@@ -520,7 +592,7 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
 // host side
 // block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25
 // (dgb_set_kernel_path(300 + mask); the default follows the measurements in profiles/)
-int g_chain_mask = 1;
+int g_chain_mask = 11;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : 0;
@@ -537,60 +609,104 @@ static long long chain_dir_len(int b, const Stencil &S_) {
     return 0;
 }
 
-template <int B, int W>
-static int chain_launch_w(const double *rec, double *x, double *mbox, Stencil S_, int dir, const int32_t *skip,
-                          cudaStream_t st) {
+int g_chain_cluster = 8;        // CTAs per cluster of the chain kernel (tuning: dgb_set_kernel_path(400 + n))
+
+template <int B, int W, int DIR>
+static int chain_launch_d(const double *rec, double *rec_other, double *x, double *mbox, Stencil S_,
+                          const int32_t *skip, cudaStream_t st) {
     using C = ChainCfg<B>;
     static bool configured = false;
+    static int max_cluster = 1;
+    auto kern = k_gs_chain<B, W, DIR>;
     if (!configured) {
-        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_chain<B, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::smem(W)));
-        DGB_CUDA_OK(cudaFuncSetAttribute(k_gs_chain<B, W, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C::smem(W)));
+        DGB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(W)));
+        // largest cluster size (<= 8, the portable limit) the device can co-schedule with this much shared memory
+        for (int cs = 8; cs >= 1; cs >>= 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs, 1, 1);
+            cfg.blockDim = dim3(W * 32, 1, 1);
+            cfg.dynamicSmemBytes = C::smem(W);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
+                max_cluster = cs;
+                break;
+            }
+            (void)cudaGetLastError();
+        }
         configured = true;
     }
     DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
     const int nbands = (S_.ja1 - S_.ja0 + C::R - 1) / C::R;
-    const int grid = (nbands + W - 1) / W;
-    if (dir > 0)
-        k_gs_chain<B, W, 1><<<grid, W * 32, C::smem(W), st>>>(rec, x, mbox, S_, work_ptr(), err_ptr(), skip);
-    else
-        k_gs_chain<B, W, -1><<<grid, W * 32, C::smem(W), st>>>(rec, x, mbox, S_, work_ptr(), err_ptr(), skip);
+    const int nctas = (nbands + W - 1) / W;
+    int cs = 1;
+    while (cs * 2 <= max_cluster && cs * 2 <= g_chain_cluster && cs < nctas) cs *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((nctas + cs - 1) / cs) * cs), 1, 1);
+    cfg.blockDim = dim3(W * 32, 1, 1);
+    cfg.dynamicSmemBytes = C::smem(W);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DGB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rec, rec_other, x, mbox, S_, work_ptr(), err_ptr(), skip));
     DGB_LAUNCH_OK();
     return 0;
 }
 
+template <int B, int W>
+static int chain_launch_w(const double *rec, double *rec_other, double *x, double *mbox, Stencil S_, int dir,
+                          const int32_t *skip, cudaStream_t st) {
+    return dir > 0 ? chain_launch_d<B, W, 1>(rec, rec_other, x, mbox, S_, skip, st)
+                   : chain_launch_d<B, W, -1>(rec, rec_other, x, mbox, S_, skip, st);
+}
+
+// have_c: the previous pass of this smoother call ran in the opposite direction on the same rhs and x has
+// not changed since -- its chain left this pass's c in the record stream, the helper is not needed
 template <int B>
-static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
-                        cudaStream_t st) {
+static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c,
+                        const int32_t *skip, cudaStream_t st) {
     using C = ChainCfg<B>;
     using H = HelperCfg<B>;
     const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
-    const size_t N = (size_t)op->Ni * op->Nj;
     double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
+    double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
     if (grid > sm_count() * 8) grid = sm_count() * 8;
-    if (g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
-        k_gs_helper<B><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, S_, dir, skip);
+    if (!have_c && g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
+        k_gs_helper<B><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
+                                               dir, skip);
         DGB_LAUNCH_OK();
     }
     if (g_gs_variant == 21) return 0;
-    if (B <= 9) {
-        if (g_gs_variant == 11) return chain_launch_w<B, 2>(rec, x, op->gs_mailbox, S_, dir, skip, st);
-    }
-    return chain_launch_w<B, C::WDEF>(rec, x, op->gs_mailbox, S_, dir, skip, st);
+    if (B <= 9 && g_gs_variant == 11) return chain_launch_w<B, 2>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
+    return chain_launch_w<B, C::WDEF>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
 }
 
-int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
+// the opposite-direction c left behind by a chain pass is complete only when no neighbour lives in a ghost row
+bool chain_c_recurrence(int flags) { return (flags & (DGB_FLAG_GHOST_LO | DGB_FLAG_GHOST_HI)) == 0; }
+
+int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c, const int32_t *skip,
                   cudaStream_t st) {
     int rc = ensure_work(0);
     if (rc) return rc;
+    if (!chain_c_recurrence(op->stencil)) have_c = false;
     switch (op->b) {
-    case 4: return chain_pass_t<4>(op, rhs, x, dir, skip, st);
-    case 9: return chain_pass_t<9>(op, rhs, x, dir, skip, st);
-    case 16: return chain_pass_t<16>(op, rhs, x, dir, skip, st);
-    case 25: return chain_pass_t<25>(op, rhs, x, dir, skip, st);
+    case 4: return chain_pass_t<4>(op, rhs, x, dir, have_c, skip, st);
+    case 9: return chain_pass_t<9>(op, rhs, x, dir, have_c, skip, st);
+    case 16: return chain_pass_t<16>(op, rhs, x, dir, have_c, skip, st);
+    case 25: return chain_pass_t<25>(op, rhs, x, dir, have_c, skip, st);
     }
     set_error("gs_chain_pass: unsupported block size b=%d", op->b);
     return 2;

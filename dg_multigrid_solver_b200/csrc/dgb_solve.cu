@@ -369,7 +369,7 @@ int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double
 enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
 // chained lexicographic GS (dgb_chain.cu)
 bool chain_supported(int b, int flags);
-int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, const int32_t *skip,
+int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c, const int32_t *skip,
                   cudaStream_t st);
 
 // kernels that need the closed-form DG stencil (k_gs_rows)
@@ -386,6 +386,11 @@ static int check_op(const dgb_operator *op) {
     return 0;
 }
 }  // namespace dgb
+
+extern "C" {
+static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
+                              const int32_t *skip, cudaStream_t st, bool have_c = false);
+}
 
 namespace dgb {
 // Relaxation.block_gauss_seidel_pyamg on the device (dgfem/relaxation.py:198-218).  r_keep (optional): every
@@ -407,13 +412,17 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         if (rc) return rc;
     }
     const int32_t *skip = check_residual ? &ctl->skip : nullptr;
+    DGB_ARG(op->dinv && rhs && u);
+    int last_dir = 0;      // direction of the previous lexicographic pass of this call (u untouched since)
     for (int it = 0; it < max_iterations; ++it) {
-        if (direction >= 0) {
-            rc = dgb_block_gs_pass(op, rhs, u, +1, mode, skip, stream);
-            if (rc) return rc;
-        }
-        if (direction <= 0) {
-            rc = dgb_block_gs_pass(op, rhs, u, -1, mode, skip, stream);
+        for (int dir = +1; dir >= -1; dir -= 2) {
+            if ((dir > 0 && direction < 0) || (dir < 0 && direction > 0)) continue;
+            if (mode == DGB_GS_LEXICOGRAPHIC) {
+                rc = ::lexicographic_pass(op, rhs, u, 1.0, dir, skip, (cudaStream_t)stream, last_dir == -dir);
+                last_dir = dir;
+            } else {
+                rc = dgb_block_gs_pass(op, rhs, u, dir, mode, skip, stream);
+            }
             if (rc) return rc;
         }
         if (check_residual) {
@@ -545,11 +554,12 @@ static int wavefront_pass(const dgb_operator *op, const double *rhs, double *x, 
 }
 
 // exact lexicographic order, either kernel family
+// have_c: see gs_chain_pass (only the smoother loop below, which knows the pass sequence, sets it)
 static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
-                              const int32_t *skip, cudaStream_t st) {
+                              const int32_t *skip, cudaStream_t st, bool have_c) {
     if (use_stream(op) && omega == 1.0 && op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
         chain_supported(op->b, op->stencil))
-        return gs_chain_pass(op, rhs, x, direction, skip, st);
+        return gs_chain_pass(op, rhs, x, direction, have_c, skip, st);
     if (use_stream(op) && op->gs_data != nullptr && op->gs_mailbox != nullptr)
         return gs_rows_launch(op->b, op->gs_data, rhs, x, op->gs_mailbox, op->Ni, op->Nj, op->stencil, direction,
                               omega, skip, st);

@@ -1018,6 +1018,7 @@ static int gs_rows_launch_c(const double *gs, const double *rhs, double *x, doub
 }
 int g_gs_variant = 0;   // experiment switch (DGB_GS_VARIANT)
 extern int g_chain_mask;
+extern int g_chain_cluster;
 template <int B>
 static int gs_rows_launch_t(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
                             double omega, const int32_t *skip, cudaStream_t st) {
@@ -1047,6 +1048,7 @@ int dgb_set_kernel_path(int32_t path) {
     if (path >= 100 && path < 200) g_gs_variant = path - 100;      // tuning experiments only
     if (path >= 200 && path < 300) g_kstream_min_b = path - 200;
     if (path >= 300 && path < 316) g_chain_mask = path - 300;      // block sizes of the chained GS kernel
+    if (path >= 400 && path <= 408) g_chain_cluster = path - 400;  // CTAs per cluster of the chained GS kernel
     return old;
 }
 

@@ -379,7 +379,7 @@ def test_chained_gauss_seidel_kernel(Ni, Nj, P):
         L.dgb_set_kernel_path(300 + CHAIN_MASK_DEFAULT)
 
 
-CHAIN_MASK_DEFAULT = 1
+CHAIN_MASK_DEFAULT = 11
 
 
 def _chained_gs_checks(grid, Ni, Nj, L):
@@ -392,7 +392,9 @@ def _chained_gs_checks(grid, Ni, Nj, L):
     rhs = rng.standard_normal(A.shape[0])
     x0 = rng.standard_normal(A.shape[0])
     Dinv = grid.d_dinv.cpu().numpy()
-    for direction, sweeps in (("forward", [1]), ("backward", [-1]), ("symmetric", [1, -1])):
+    # 3 symmetric iterations: passes 2..6 take their c from the previous pass's chain (no helper launch)
+    for direction, sweeps in (("forward", [1]), ("backward", [-1]), ("symmetric", [1, -1]),
+                              ("symmetric", [1, -1] * 3), ("forward", [1] * 2)):
         ref = x0.copy()
         N = Ni * Nj
         for sw in sweeps:
@@ -402,7 +404,8 @@ def _chained_gs_checks(grid, Ni, Nj, L):
         try:
             for path in (0, 1):
                 L.dgb_set_kernel_path(path)
-                got[path] = Relaxation.block_gauss_seidel_pyamg(grid, rhs, x0, direction, 1, 1)
+                iters = len(sweeps) // (2 if direction == "symmetric" else 1)
+                got[path] = Relaxation.block_gauss_seidel_pyamg(grid, rhs, x0, direction, 1, iters)
         finally:
             L.dgb_set_kernel_path(0)
         assert L.dgb_device_error(1) == 0

@@ -74,6 +74,8 @@ def main():
     }
     if os.environ.get("DGB_KSTREAM_MIN_B"):
         L.dgb_set_kernel_path(200 + int(os.environ["DGB_KSTREAM_MIN_B"]))
+    if os.environ.get("DGB_CHAIN_CLUSTER"):
+        L.dgb_set_kernel_path(400 + int(os.environ["DGB_CHAIN_CLUSTER"]))
     if os.environ.get("DGB_GS_VARIANT"):
         L.dgb_set_kernel_path(100 + int(os.environ["DGB_GS_VARIANT"]))
     for path, nm in ((0, "stream"), (1, "generic")):
