@@ -282,17 +282,54 @@ def run_b200(args):
     mode = _lib.GS_REDBLACK if args.gs_mode == "redblack" else _lib.GS_LEXICOGRAPHIC
     xg = u_k.clone()
     k_gs = timed(lambda: _lib.call("dgb_block_gs_pass", op, fine.d_rhs, xg, 1, mode, None, st), reps=3)
+    # the smoother as the V-cycle calls it (symmetric sweeps, no residual test here): with the chained kernel only
+    # the first pass of a call launches the dependency-free helper, every later pass is the chain kernel alone
+    ctl0 = H["ctl"]
+    sm1 = timed(lambda: _lib.call("dgb_block_gauss_seidel_pyamg", op, fine.d_rhs, xg, 0, 1, mode, 0, ctl0, ws_part,
+                                  ws_sum, st), reps=3)
+    sm3 = timed(lambda: _lib.call("dgb_block_gauss_seidel_pyamg", op, fine.d_rhs, xg, 0, 3, mode, 0, ctl0, ws_part,
+                                  ws_sum, st), reps=2)
+    chained = fine.d_chain is not None and mode == _lib.GS_LEXICOGRAPHIC
+    t_pass_amortised = (sm3[0] - sm1[0]) / 4.0                   # one later pass of a symmetric sweep
+    t_first = sm1[0] - t_pass_amortised                          # first pass of a call (helper + chain when chained)
     peak, peak_src = measured_peak()
     kern = {}
-    for nm, (ms, nl), nbytes in (("apply", k_apply, ab["apply"]), ("residual_norm", k_resid, ab["residual"]),
-                                 ("gs_pass", k_gs, ab["gs_pass"])):
+    ab_chain = N * (2 * b * b + 4 * b) * 8        # chain pass: 2 pre-multiplied blocks, c, d in; x, next c out
+    ab_helper = N * (3 * b * b + 5 * b) * 8       # helper: Dinv + 2 blocks, rhs, x in; c, d (both streams) out
+    rows = [("apply", k_apply, ab["apply"]), ("residual_norm", k_resid, ab["residual"]), ("gs_pass", k_gs, ab["gs_pass"])]
+    if chained:
+        rows += [("gs_chain_pass", (t_pass_amortised, 1), ab_chain),
+                 ("gs_helper", (max(k_gs[0] - t_pass_amortised, 1e-6), 1), ab_helper)]
+    else:
+        rows += [("gs_pass_in_sweep", (t_pass_amortised, k_gs[1]), ab["gs_pass"])]
+    for nm, (ms, nl), nbytes in rows:
         gbs = nbytes / (ms * 1e-3) / 1e9
         kern[nm] = {"ms": ms, "launches": nl, "algorithmic_bytes": nbytes, "GB/s": gbs, "frac": gbs / peak}
-    roofline = {"bound": "hbm", "kernel": f"block_gs_pass(fine level, b={b}, mode={args.gs_mode})",
-                "achieved": kern["gs_pass"]["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": kern["gs_pass"]["frac"], "traffic": None, "peak_source": peak_src,
-                "launches_per_pass": kern["gs_pass"]["launches"],
-                "algorithmic_bytes_per_launch_group": ab["gs_pass"]}
+    kern["smoother_symmetric_1it_ms"] = sm1[0]
+    kern["smoother_symmetric_3it_ms"] = sm3[0]
+    # share of one V-cycle spent in each fine-level kernel family (reference schedule: 2 pre + 1 post symmetric
+    # iterations = 6 passes in 2 smoother calls; 5 residual evaluations, the restriction reuses the smoother's last)
+    n_res = 5 if args.check_residual else 1
+    fam = {"residual_norm": n_res * kern["residual_norm"]["ms"]}
+    if chained:
+        fam["gs_chain_pass"] = 6 * kern["gs_chain_pass"]["ms"]
+        fam["gs_helper"] = 2 * kern["gs_helper"]["ms"]
+    else:
+        fam["gs_pass"] = 6 * kern["gs_pass"]["ms"]
+    for nm, ms in fam.items():
+        kern[nm]["share_of_vcycle"] = ms / ms_per_step
+    top = max(fam, key=fam.get)
+    names = {"residual_norm": f"k_rows<{b}, residual> (r = rhs - A u and its norm, fine level)",
+             "gs_chain_pass": f"k_gs_chain<{b}> (dependency chain of one lexicographic block-GS pass, fine level)",
+             "gs_helper": f"k_gs_helper<{b}> (dependency-free part of a block-GS pass, fine level)",
+             "gs_pass": f"block_gs_pass(fine level, b={b}, mode={args.gs_mode})"}
+    roofline = {"bound": "hbm", "kernel": names[top], "achieved": kern[top]["GB/s"], "peak": peak, "unit": "GB/s",
+                "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
+                "share_of_vcycle": kern[top]["share_of_vcycle"],
+                "launches_per_call": kern[top]["launches"],
+                "algorithmic_bytes_per_launch_group": kern[top]["algorithmic_bytes"],
+                "other_kernels": {nm: {"frac": kern[nm]["frac"], "share_of_vcycle": kern[nm]["share_of_vcycle"]}
+                                  for nm in fam if nm != top}}
     # V-cycle level traffic: reference schedule = 12 passes/level (+ transfers, ignored)
     vbytes = 0
     for g in d.grids[1:]:
