@@ -497,15 +497,20 @@ struct HelperCfg {
     static constexpr int NT = ((EPB * B + 31) / 32) * 32;
 };
 
-template <int B>
+// RES: also evaluate the full residual r = rhs - A x (optionally stored) and its sum of squares (one partial per
+// CTA) -- the smoother's entry residual test (dgfem/relaxation.py:202) shares the block reads of the first pass.
+template <int B, bool RES>
 __global__ void __launch_bounds__(HelperCfg<B>::NT)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
-            double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip) {
+            double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
+            double *partials) {
     constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
     if (skip != nullptr && *skip != 0) return;
     __shared__ double s_rsum[EPB * B];
     __shared__ double s_rhs[EPB * B];
+    __shared__ double s_red[32];
+    double sumsq = 0.0;
     const int el = threadIdx.x / B, r = threadIdx.x - el * B;
     const int Ni = S_.Ni;
     const int first = S_.ja0 * Ni, count = (S_.ja1 - S_.ja0) * Ni;
@@ -517,18 +522,25 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             const int j = e / Ni, i = e - j * Ni;
             const int e_row = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;       // handled by the chain
             const int e_up = S_.active(j - dir) ? e - dir * Ni : -1;               // handled by the chain
-            double acc = 0.0;
+            double acc = 0.0, acc_chain = 0.0;
             for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
                 const int col = indices[jj];
-                if (col == e || col == e_row || col == e_up) continue;
+                const bool chain_part = col == e || col == e_row || col == e_up;
+                if (!RES && chain_part) continue;
                 const double *a = data + ((size_t)jj * B + r) * B;
                 const double *xv = x + (size_t)col * B;
                 double tt = 0.0;
 #pragma unroll
                 for (int c = 0; c < B; ++c) tt = fma(a[c], xv[c], tt);
-                acc += tt;
+                if (chain_part) acc_chain += tt;
+                else acc += tt;
             }
             const double f = rhs[(size_t)e * B + r];
+            if (RES) {
+                const double res = f - (acc + acc_chain);
+                if (r_out != nullptr) r_out[(size_t)e * B + r] = res;
+                sumsq = fma(res, res, sumsq);
+            }
             s_rhs[el * B + r] = f;
             s_rsum[el * B + r] = f - acc;
         }
@@ -548,6 +560,10 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             rec_other[(size_t)chain_loc<B>(S_, -dir, i, j) * REC + 2 * B2 + B + r] = td;
         }
         __syncthreads();
+    }
+    if (RES) {
+        const double t = block_sum<HelperCfg<B>::NT>(sumsq, s_red);
+        if (threadIdx.x == 0) partials[blockIdx.x] = t;
     }
 }
 
@@ -685,13 +701,44 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
     int grid = (count + H::EPB - 1) / H::EPB;
     if (grid > sm_count() * 8) grid = sm_count() * 8;
     if (!have_c && g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
-        k_gs_helper<B><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
-                                               dir, skip);
+        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
+                                                      S_, dir, skip, nullptr, nullptr);
         DGB_LAUNCH_OK();
     }
     if (g_gs_variant == 21) return 0;
     if (B <= 9 && g_gs_variant == 11) return chain_launch_w<B, 2>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
     return chain_launch_w<B, C::WDEF>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
+}
+
+// helper of the pass in direction `dir` fused with the residual r = rhs - A x (r may be NULL) and its per-CTA
+// sums of squares; *grid_out = number of partials written
+template <int B>
+static int helper_residual_t(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
+                             double *partials, int *grid_out, cudaStream_t st) {
+    using H = HelperCfg<B>;
+    const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
+    double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
+    double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
+    const int count = (S_.ja1 - S_.ja0) * S_.Ni;
+    int grid = (count + H::EPB - 1) / H::EPB;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (grid > kMaxPartials) grid = kMaxPartials;
+    k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
+                                                 dir, nullptr, r, partials);
+    DGB_LAUNCH_OK();
+    *grid_out = grid;
+    return 0;
+}
+int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
+                             double *partials, int *grid_out, cudaStream_t st) {
+    switch (op->b) {
+    case 4: return helper_residual_t<4>(op, rhs, x, dir, r, partials, grid_out, st);
+    case 9: return helper_residual_t<9>(op, rhs, x, dir, r, partials, grid_out, st);
+    case 16: return helper_residual_t<16>(op, rhs, x, dir, r, partials, grid_out, st);
+    case 25: return helper_residual_t<25>(op, rhs, x, dir, r, partials, grid_out, st);
+    }
+    set_error("gs_chain_helper_residual: unsupported block size b=%d", op->b);
+    return 2;
 }
 
 // the opposite-direction c left behind by a chain pass is complete only when no neighbour lives in a ghost row

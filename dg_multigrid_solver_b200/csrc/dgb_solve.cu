@@ -371,6 +371,9 @@ enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
 bool chain_supported(int b, int flags);
 int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c, const int32_t *skip,
                   cudaStream_t st);
+bool chain_c_recurrence(int flags);
+int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
+                             double *partials, int *grid_out, cudaStream_t st);
 
 // kernels that need the closed-form DG stencil (k_gs_rows)
 static bool use_stream(const dgb_operator *op) {
@@ -405,15 +408,29 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
     DGB_ARG(ctl && partials && sumsq);
     DGB_ARG(direction == 0 || direction == 1 || direction == -1);
     const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
+    DGB_ARG(op->dinv && rhs && u);
+    int last_dir = 0;      // direction of the previous lexicographic pass of this call (u untouched since)
     if (check_residual) {
-        rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, nullptr, stream);
-        if (rc) return rc;
+        const int first_dir = direction >= 0 ? +1 : -1;
+        const bool chained = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
+                             op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
+                             chain_supported(op->b, op->stencil) && chain_c_recurrence(op->stencil);
+        if (chained) {
+            // the entry residual shares its block reads with the dependency-free part of the first pass
+            int grid = 1;
+            rc = gs_chain_helper_residual(op, rhs, u, first_dir, r_keep, partials, &grid, (cudaStream_t)stream);
+            if (rc) return rc;
+            k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, nullptr);
+            DGB_LAUNCH_OK();
+            last_dir = -first_dir;          // the first pass finds its c in place
+        } else {
+            rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, nullptr, stream);
+            if (rc) return rc;
+        }
         rc = dgb_smoother_begin(ctl, sumsq, n, stream);
         if (rc) return rc;
     }
     const int32_t *skip = check_residual ? &ctl->skip : nullptr;
-    DGB_ARG(op->dinv && rhs && u);
-    int last_dir = 0;      // direction of the previous lexicographic pass of this call (u untouched since)
     for (int it = 0; it < max_iterations; ++it) {
         for (int dir = +1; dir >= -1; dir -= 2) {
             if ((dir > 0 && direction < 0) || (dir < 0 && direction > 0)) continue;

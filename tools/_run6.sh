@@ -6,5 +6,5 @@ import json
 for f in ('gpurun_out/bench_a.json',):
     for l in open(f):
         if l.startswith('{'):
-            d=json.loads(l); print(f, d['ms_per_step'], d['e2e']['value'], {k:v['ms'] for k,v in d['kernels'].items()}, d['vcycle']['normalised_residual_after_timed_cycles'], d['gpu_launches'])
+            d=json.loads(l); print(f, d['ms_per_step'], d['e2e']['value'], {k:v['ms'] for k,v in d['kernels'].items() if isinstance(v,dict)}, d['vcycle']['normalised_residual_after_timed_cycles'], d['gpu_launches'])
 PY
