@@ -527,11 +527,7 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
                 const int col = indices[jj];
                 const bool chain_part = col == e || col == e_row || col == e_up;
                 if (!RES && chain_part) continue;
-                const double *a = data + ((size_t)jj * B + r) * B;
-                const double *xv = x + (size_t)col * B;
-                double tt = 0.0;
-#pragma unroll
-                for (int c = 0; c < B; ++c) tt = fma(a[c], xv[c], tt);
+                const double tt = row_dot<B>(data + ((size_t)jj * B + r) * B, x + (size_t)col * B);
                 if (chain_part) acc_chain += tt;
                 else acc += tt;
             }

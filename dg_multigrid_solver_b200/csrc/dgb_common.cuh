@@ -64,6 +64,40 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         return 2;                                                                       \
     }
 
+// sum_c a[c] * x[c], c = 0..B-1 in order (scipy's bsr_matvec accumulation order), with the matrix row read in
+// aligned 16-byte pieces.  Rows of an odd-b block start at 8 (mod 16) every other row: the aligned window then
+// begins one double early / ends one double late, and the stray entry meets a zero factor.  (A warp of these row
+// reads touches every 128-byte line once per 16-byte piece instead of once per double -- the L1 tag stage, not
+// HBM, bounded the 8-byte version.)  The stray entry is always inside the array or its 16-byte slack.
+template <int B>
+__device__ __forceinline__ double row_dot(const double *__restrict__ a, const double *__restrict__ x) {
+    double t = 0.0;
+    if (B == 1) {
+        t = a[0] * x[0];
+    } else if (B % 2 == 0) {
+        const double2 *a2 = reinterpret_cast<const double2 *>(a);
+#pragma unroll
+        for (int k = 0; k < B / 2; ++k) {
+            const double2 v = a2[k];
+            t = fma(v.x, x[2 * k], t);
+            t = fma(v.y, x[2 * k + 1], t);
+        }
+    } else {
+        const int mis = (int)((reinterpret_cast<uintptr_t>(a) >> 3) & 1);
+        const double2 *a2 = reinterpret_cast<const double2 *>(a - mis);
+#pragma unroll
+        for (int k = 0; k < (B + 1) / 2; ++k) {
+            const double2 v = a2[k];
+            const int c0 = 2 * k - mis, c1 = c0 + 1;
+            const double x0 = (c0 >= 0 && c0 < B) ? x[c0] : 0.0;
+            const double x1 = (c1 < B) ? x[c1] : 0.0;
+            t = fma(v.x, x0, t);
+            t = fma(v.y, x1, t);
+        }
+    }
+    return t;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -88,12 +88,7 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
             for (int jj = j0; jj < j1; ++jj) {
                 const int col = indices[jj];
                 if (MODE == MODE_RELAX && col == e) continue;
-                const double *a = data + ((size_t)jj * B + r) * B;
-                const double *xv = x_in + (size_t)col * B;
-                double t = 0.0;
-#pragma unroll
-                for (int c = 0; c < B; ++c) t = fma(a[c], xv[c], t);
-                acc += t;
+                acc += row_dot<B>(data + ((size_t)jj * B + r) * B, x_in + (size_t)col * B);
             }
         }
         if (MODE == MODE_APPLY) {
@@ -108,10 +103,7 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
             if (e >= 0) s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
             __syncthreads();
             if (e >= 0) {
-                const double *d = dinv + ((size_t)e * B + r) * B;
-                double t = 0.0;
-#pragma unroll
-                for (int c = 0; c < B; ++c) t = fma(d[c], s_rsum[el * B + c], t);
+                const double t = row_dot<B>(dinv + ((size_t)e * B + r) * B, s_rsum + el * B);
                 const double xo = x_in[(size_t)e * B + r];
                 x_out[(size_t)e * B + r] = (omega == 1.0) ? t : omega * t + (1.0 - omega) * xo;
             }

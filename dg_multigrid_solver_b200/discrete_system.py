@@ -108,7 +108,7 @@ def prepare_smoother_data(grid):
     b = grid.d_data.shape[1]
     N = grid.d_indptr.numel() - 1
     st = _lib.stream_ptr()
-    grid.d_dinv = torch.empty((N, b, b), dtype=torch.float64, device="cuda")
+    grid.d_dinv = padded_blocks(N, b)              # 16 bytes of slack: rows are read in aligned 16-byte pieces
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("dgb_block_diag_inverse", grid.d_data, grid.d_indices, grid.d_indptr, N, b, grid.d_dinv, info, st)
     grid._dinv_info = info

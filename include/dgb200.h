@@ -62,9 +62,11 @@ typedef struct dgb_smoother_ctl {
  * `stencil` selects the kernel family:
  *   -1  arbitrary BSR matrix (Ni*Nj block rows): generic row-per-thread kernels;
  *   >=0 the DG 5-point block stencil on the Ni x Nj element grid, value = DGB_FLAG_PERIODIC_I|J
- *       bits, structure verified once with dgb_check_stencil: the TMA-streaming kernels are
- *       used.  They need 16 bytes of readable slack behind data / gs_data (bulk copies are
- *       16-byte aligned) and gs_data for the smoothers (else the generic kernels run). */
+ *       (| DGB_FLAG_GHOST_LO|HI) bits, structure verified once with dgb_check_stencil: the
+ *       single-launch lexicographic smoother kernels are used (gs_chain or gs_data, plus
+ *       gs_mailbox; else the generic kernels run).
+ * `data`, `dinv` (and gs_data) need 16 bytes of readable slack behind the last block: all kernels
+ * read matrix rows in aligned 16-byte pieces. */
 typedef struct dgb_operator {
     int32_t Ni, Nj;          /* element grid; N = Ni*Nj block rows                        */
     int32_t b, nnzb;         /* block size, number of stored blocks                        */
