@@ -36,16 +36,20 @@ extern int g_gs_variant;
 template <int B>
 struct ChainCfg {
     static constexpr int B2 = B * B;
-    static constexpr int R = 32 / B;                                  // element rows per warp
+    static constexpr int P = B == 9 ? 3 : 1;                          // lanes per scalar row (each takes B/P columns)
+    static constexpr int CW = B / P;                                  // matrix columns per lane
+    static constexpr int LPR = B * P;                                 // lanes per element row
+    static constexpr int R = 32 / LPR;                                // element rows per warp
+    static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
-    static constexpr int CH = B <= 4 ? 8 : B <= 9 ? 4 : B <= 16 ? 2 : 1;   // steps per chunk (one bulk copy)
+    static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 2 : 1;           // steps per chunk (one bulk copy)
     static constexpr int NS = 3;                                      // bulk-copy stages
     static constexpr int RING = B <= 4 ? 32 : 16;                     // columns per band hand-over ring
     static constexpr int RINGR = CH < 2 ? 2 : CH;                     // steps per row ring (rows of one warp)
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
-    static constexpr int WDEF = (B <= 4 || B == 16) ? 3 : 4;          // warps (bands) per CTA (shared memory bound)
+    static constexpr int WDEF = B == 9 ? 6 : (B <= 4 || B == 16) ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
     static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
     static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
@@ -76,61 +80,82 @@ __device__ __forceinline__ void sts1(uint32_t a, double v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
-// one ring slot (BP doubles) into registers; *any_sentinel: some entry is the all-ones "not delivered" mark
+// my part of one ring slot into registers (the whole slot when P == 1, else columns [part*CW, part*CW+CW): `a`
+// already points at my part); *any_sentinel: some entry is the all-ones "not delivered" mark
 template <int B>
-__device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<B>::BP], bool *any_sentinel) {
-    constexpr int BP = ChainCfg<B>::BP;
+__device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<B>::VN], bool *any_sentinel) {
+    constexpr int VN = ChainCfg<B>::VN, P = ChainCfg<B>::P;
+    if (VN % 2 == 0) {
 #pragma unroll
-    for (int c = 0; c < BP; c += 2) {
-        const double2 t = lds2(a + c * 8);
-        v[c] = t.x;
-        v[c + 1] = t.y;
+        for (int c = 0; c < VN; c += 2) {
+            const double2 t = lds2(a + c * 8);
+            v[c] = t.x;
+            v[c + 1 < VN ? c + 1 : c] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < VN; ++c) v[c] = lds1(a + c * 8);
     }
     if (any_sentinel != nullptr) {
         unsigned mx = 0u;
 #pragma unroll
-        for (int c = 0; c < B; ++c) mx = max(mx, (unsigned)__double2hiint(v[c]));
+        for (int c = 0; c < (P == 1 ? B : VN); ++c) mx = max(mx, (unsigned)__double2hiint(v[c]));
         *any_sentinel = mx == 0xffffffffu;
     }
 }
 
-// my rows of the two (negated) pre-multiplied blocks and my entry of c, from the staged record
+// my part of my rows of the two (negated) pre-multiplied blocks and my entries of c and d, from the staged record
 template <int B>
 struct ChainRow {
-    double ml[B], mu[B], c, d;
+    static constexpr int VN = ChainCfg<B>::VN, P = ChainCfg<B>::P, CW = ChainCfg<B>::CW;
+    double ml[CW], mu[CW], c, d;
     __device__ __forceinline__ void load(uint32_t rm, uint32_t rc) {
         constexpr int B2 = B * B;
         c = lds1(rc);
         d = lds1(rc + B * 8);
-        if (B % 2 == 0) {
+        if (P == 1 && B % 2 == 0) {
 #pragma unroll
-            for (int k = 0; k < B; k += 2) {
+            for (int k = 0; k < CW; k += 2) {
                 const double2 m0 = lds2(rm + k * 8), m1 = lds2(rm + (B2 + k) * 8);
-                ml[k] = m0.x; ml[k + 1 < B ? k + 1 : k] = m0.y;
-                mu[k] = m1.x; mu[k + 1 < B ? k + 1 : k] = m1.y;
+                ml[k] = m0.x; ml[k + 1 < CW ? k + 1 : k] = m0.y;
+                mu[k] = m1.x; mu[k + 1 < CW ? k + 1 : k] = m1.y;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < B; ++k) {
+            for (int k = 0; k < CW; ++k) {
                 ml[k] = lds1(rm + k * 8);
                 mu[k] = lds1(rm + (B2 + k) * 8);
             }
         }
     }
-    // x = c - M_row x_prev - M_up x_up   (records hold the negated products)
-    __device__ __forceinline__ double eval(const double (&p)[ChainCfg<B>::BP], const double (&u)[ChainCfg<B>::BP]) const {
-        double a0 = c, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // x = c - M_row x_prev - M_up x_up   (records hold the negated products); with P > 1 the partial sums of the
+    // P lanes of a scalar row are added by shuffles and the result is valid in the lane with part == 0
+    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN]) const {
+        if (P == 1) {
+            double a0 = c, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            if (k & 1) {
-                a1 = fma(ml[k], p[k], a1);
-                a3 = fma(mu[k], u[k], a3);
-            } else {
-                a0 = fma(ml[k], p[k], a0);
-                a2 = fma(mu[k], u[k], a2);
+            for (int k = 0; k < CW; ++k) {
+                if (k & 1) {
+                    a1 = fma(ml[k], p[k], a1);
+                    a3 = fma(mu[k], u[k], a3);
+                } else {
+                    a0 = fma(ml[k], p[k], a0);
+                    a2 = fma(mu[k], u[k], a2);
+                }
             }
+            return (a0 + a1) + (a2 + a3);
         }
-        return (a0 + a1) + (a2 + a3);
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < CW; ++k) {
+            s1 = fma(ml[k], p[k], s1);
+            s2 = fma(mu[k], u[k], s2);
+        }
+        const double mine = s1 + s2;
+        double sum = mine;
+#pragma unroll
+        for (int o = 1; o < P; ++o) sum += __shfl_down_sync(0xffffffffu, mine, o);
+        return c + sum;
     }
 };
 
@@ -217,6 +242,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     using C = ChainCfg<B>;
     constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP;
     constexpr int RINGR = C::RINGR, WR = C::WR, RRS = C::RRS, PCH = C::PCH, PSL = C::PSL;
+    constexpr int P = C::P, CW = C::CW, LPR = C::LPR, VN = C::VN;
     constexpr uint32_t S = BP * 8;                 // bytes per ring slot
     constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
@@ -255,10 +281,14 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     if (sr0 >= nrows) return;
     const int Rv = min(R, nrows - sr0);            // rows of this band
     uint64_t *full = bars + w * NS;
-    const int g = lane / B, r = lane - g * B;
+    // lane -> (element row g of the band, scalar row r, column part): lanes beyond the band's rows shadow row 0
+    // (they load and compute, every store of theirs goes to a scratch area)
+    const int g = lane / LPR, rem = lane - g * LPR;
+    const int r = rem / P, part = rem - r * P;
     const bool live = g < Rv;
-    const int gq = live ? g : 0;                   // idle lanes shadow row 0 (same values, never stored to x)
-    const bool g0 = live && g == 0, lastg = live && g == R - 1;
+    const int gq = live ? g : 0;
+    const bool fin = live && part == 0;            // this lane holds the finished x_r of its row
+    const bool g0 = live && g == 0, lastg = fin && g == R - 1;
     const int j = DIR > 0 ? S_.ja0 + sr0 + gq : S_.ja1 - 1 - sr0 - gq;
     const int j0 = DIR > 0 ? S_.ja0 + sr0 : S_.ja1 - 1 - sr0;
     const int T = Ni + Rv - 1;                     // steps: row g handles sweep index t - g at step t
@@ -338,13 +368,14 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     // last row -> next band's incoming ring (shared::cluster address: this CTA's, or warp 0 of the next CTA)
     uint32_t out_w = lastg ? (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank)) + 8 * r
                            : cluster_map(scr, crank) + 8 * lane;
+    const uint32_t po = (uint32_t)(part * CW * 8);                     // my columns inside a ring slot
     const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
                                          : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
-    uint32_t sen_w = first_row ? in_b + 8 * r : scr + 8 * lane;        // row 0 hands the incoming slot back
-    uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B) * 8);      // my matrix rows, stage 0 step 0
+    uint32_t sen_w = (fin && first_row) ? in_b + 8 * r : scr + 8 * lane;         // row 0 hands the incoming slot back
+    uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B + part * CW) * 8);   // my matrix entries, stage 0 step 0
     uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
-    uint32_t own_w = own_b + 8 * r;
-    const uint32_t first_mask = first_row ? 0xffffffffu : 0u;
+    uint32_t own_w = fin ? own_b + 8 * r : scr + 8 * lane;
+    const uint32_t first_mask = (fin && first_row) ? 0xffffffffu : 0u;
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
     asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
@@ -395,13 +426,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
             if (RINGR == CH) {
                 ua0 = first_row ? in_b + si0 : up_b + (RINGR - 1) * S;
                 ua = first_row ? in_b + si0 : up_b - S;
-                pa0 = own_b + (RINGR - 1) * S;
-                pa = own_b - S;
+                pa0 = own_b + (RINGR - 1) * S + po;
+                pa = own_b - S + po;
                 ow = own_w;
             } else {        // CH == 1: two-slot row rings
                 ua0 = first_row ? in_b + si0 : up_b + (S - sr0b);
                 ua = ua0;
-                pa0 = own_b + (S - sr0b);
+                pa0 = own_b + (S - sr0b) + po;
                 pa = pa0;
                 ow = own_w + sr0b;
             }
@@ -415,18 +446,18 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
             asm volatile("" : "+l"(xp), "+l"(cop));
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
-                const uint32_t uk = k == 0 ? ua0 : ua + k * S;
-                double u[BP], p[BP];
+                const uint32_t uk = k == 0 ? ua0 : ua + k * S;     // slot of the row above
+                double u[VN], p[VN];
                 ChainRow<B> row;
                 bool bad;
-                chain_load_vec<B>(uk, u, &bad);
+                chain_load_vec<B>(uk + po, u, &bad);
                 chain_load_vec<B>(k == 0 ? pa0 : pa + k * S, p, nullptr);
                 row.load(sm + k * KS, sc + k * KS);
                 const bool wait_up = __any_sync(FULL, bad);        // the neighbour band has not delivered yet?
                 double xnew = row.eval(p, u);
                 if (__builtin_expect(wait_up, 0)) {
                     if (!chain_wait_up<B>(uk, err)) return;
-                    chain_load_vec<B>(uk, u, nullptr);
+                    chain_load_vec<B>(uk + po, u, nullptr);
                     xnew = row.eval(p, u);
                 }
                 sts1(sw + k * S, sentinel);
@@ -434,7 +465,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
                 sts1_cluster(oa, xnew);
                 oa += S;
                 if (oa == oend) oa = out_w;
-                if (live) {
+                if (fin) {
                     stg1(xp + k * DIR * B, xnew);
                     stg1(cop + k * COS, (row.d - row.c) + xnew);       // the next (opposite) pass's c
                 }
@@ -446,25 +477,25 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
             for (int k = 0; k < CH && t0 + k < T; ++k) {
                 const int t = t0 + k;
                 const int idx = t - gq;
-                const bool act = live && idx >= 0 && idx < Ni;
+                const bool act = fin && idx >= 0 && idx < Ni;
                 const bool poll = g0 && t < Ni;
                 const uint32_t so = (uint32_t)(t % RINGR) * S, sop = (uint32_t)((t + RINGR - 1) % RINGR) * S;
                 const uint32_t uk = first_row ? in_b + (uint32_t)(t % RING) * S : up_b + sop;
-                double u[BP], p[BP];
+                double u[VN], p[VN];
                 bool bad;
-                chain_load_vec<B>(uk, u, &bad);
-                chain_load_vec<B>(own_b + sop, p, nullptr);
+                chain_load_vec<B>(uk + po, u, &bad);
+                chain_load_vec<B>(own_b + sop + po, p, nullptr);
                 int spin = 0;
                 while (__any_sync(FULL, poll && bad)) {
-                    chain_load_vec<B>(uk, u, &bad);
+                    chain_load_vec<B>(uk + po, u, &bad);
                     if (spin_fail(spin)) return;
                 }
                 ChainRow<B> row;
                 row.load(sm + k * KS, sc + k * KS);
                 const double xnew = row.eval(p, u);
-                if (poll) sts1(uk + 8 * r, sentinel);
+                if (poll && fin) sts1(uk + 8 * r, sentinel);
                 if (act) {
-                    sts1(own_w + so, xnew);
+                    sts1(own_b + so + 8 * r, xnew);
                     if (lastg) sts1_cluster(out_w + (uint32_t)(idx % RING) * S, xnew);
                     xrow[(size_t)(DIR > 0 ? idx : Ni - 1 - idx) * B] = xnew;
                     corow[(long long)idx * COS] = (row.d - row.c) + xnew;
