@@ -43,22 +43,22 @@ struct ChainCfg {
     static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
     static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 2 : 1;           // steps per chunk (one bulk copy)
-    static constexpr int NS = 3;                                      // bulk-copy stages
-    static constexpr int RING = B <= 4 ? 32 : 16;                     // columns per band hand-over ring
+    static constexpr int NS = B == 9 ? 2 : 3;                         // bulk-copy stages
+    static constexpr int RING = B <= 9 ? 32 : 16;                     // columns per band hand-over ring
     static constexpr int RINGR = CH < 2 ? 2 : CH;                     // steps per row ring (rows of one warp)
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
-    static constexpr int WDEF = B == 9 ? 6 : (B <= 4 || B == 16) ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
+    static constexpr int WDEF = B == 9 ? 8 : (B <= 4 || B == 16) ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
     static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
     static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
-    static constexpr int SCR = RING * BP + 64;                        // scratch doubles per warp: dummy store targets
+    static constexpr int SCR = RING * BP + 64;                        // scratch doubles per CTA: dummy store targets (benign races)
     __host__ __device__ static constexpr int stage_d(int W) { return W * NS * R * CH * REC; }
     __host__ __device__ static constexpr size_t o_ring(int W) { return sizeof(double) * stage_d(W); }
     // warp w: incoming ring at w * WR, then its R row rings; the CTA's outgoing ring is "warp W"'s incoming ring
     __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * WR; }
-    __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * W * SCR; }
+    __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * SCR; }
     __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * W * NS; }
     __host__ __device__ static constexpr size_t smem(int W) { return o_prog(W) + sizeof(int) * (W + 1); }
 };
@@ -227,6 +227,7 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
             if (c + 1 < B) mx = max(mx, (unsigned)__double2hiint(t.y));
         }
         bad = mx == 0xffffffffu;
+        if (bad) __nanosleep(20);       // do not steal issue slots from the producing warp on the same sub-partition
         if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
             if ((threadIdx.x & 31) == 0) atomicExch(err, 2);
             return false;
@@ -364,7 +365,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     uint32_t in_b = smem_u32(inring);
     uint32_t up_b = smem_u32(rowring + (gq > 0 ? gq - 1 : 0) * RRS);   // ring of the row above (g > 0)
     uint32_t own_b = smem_u32(rowring + gq * RRS);
-    const uint32_t scr = smem_u32(scratch + w * C::SCR);
+    const uint32_t scr = smem_u32(scratch);
     // last row -> next band's incoming ring (shared::cluster address: this CTA's, or warp 0 of the next CTA)
     uint32_t out_w = lastg ? (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank)) + 8 * r
                            : cluster_map(scr, crank) + 8 * lane;
@@ -397,6 +398,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
         return false;
     };
 
+    int prog_seen = 0;
     for (int n = 0; n < nchunks; ++n) {
         const int s = n % NS;
         const int t0 = n * CH;
@@ -404,9 +406,14 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
         // ---- once per chunk: flow control and the global hand-overs ----
         if (pred == 1 && lane == 0) s_prog[w] = t0;                           // columns < t0 are consumed
         if (succ == 1 || succ == 3) {
-            int spin = 0;
-            while (ldv_cluster_s32(prog_next) < t0 + CH - RING)
-                if (spin_fail(spin)) return;
+            // the consumer's progress as sampled one chunk ago is usually enough (the sample of a remote CTA takes
+            // about a microsecond to arrive: it must not sit on this warp's critical path every chunk)
+            if (prog_seen < t0 + CH - RING) {
+                int spin = 0;
+                while ((prog_seen = ldv_cluster_s32(prog_next)) < t0 + CH - RING)
+                    if (spin_fail(spin)) return;
+            }
+            prog_seen = ldv_cluster_s32(prog_next);      // consumed at the next chunk
         }
         if (pred != 1 && (t0 % PCH) == 0 && t0 < Ni) {
             if (pred == 2) {
