@@ -323,8 +323,17 @@ def run_b200(args):
              "gs_chain_pass": f"k_gs_chain<{b}> (dependency chain of one lexicographic block-GS pass, fine level)",
              "gs_helper": f"k_gs_helper<{b}> (dependency-free part of a block-GS pass, fine level)",
              "gs_pass": f"block_gs_pass(fine level, b={b}, mode={args.gs_mode})"}
+    # DRAM traffic of the dominant kernel from one `ncu --set full` capture of the same launch (profiles/), if there
+    # is one for this workload and kernel
+    traffic, traffic_src = None, None
+    tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                         "r01_ncu_full_k_rows_b9_residual_summary.json")
+    if top == "residual_norm" and n == 2048 and p == 2 and os.path.exists(tfile):
+        with open(tfile) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/" + os.path.basename(tfile)
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": kern[top]["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "share_of_vcycle": kern[top]["share_of_vcycle"],
                 "launches_per_call": kern[top]["launches"],
                 "algorithmic_bytes_per_launch_group": kern[top]["algorithmic_bytes"],
