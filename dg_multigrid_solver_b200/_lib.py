@@ -45,7 +45,7 @@ class Level(ctypes.Structure):
 
 class VcycleOpts(ctypes.Structure):
     _fields_ = [("gs_mode", c_i32), ("check_residual", c_i32), ("coarse_iterations", c_i32),
-                ("reserved", c_i32)]
+                ("reserved", c_i32), ("u_final_event", c_vp)]
 
 
 class TablesDesc(ctypes.Structure):
@@ -115,7 +115,7 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.dgb_abi_version() != 3:
+    if L.dgb_abi_version() != 4:
         raise DgbError("libdgb200.so ABI version mismatch")
     if os.environ.get("DGB_KERNELS", "auto") == "generic":
         L.dgb_set_kernel_path(1)

@@ -394,7 +394,7 @@ namespace dgb {
 // for the restriction instead of evaluating the same residual again (dgfem/solver.py:150).
 int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direction, int32_t max_iterations,
              int32_t mode, int32_t check_residual, dgb_smoother_ctl *ctl, double *partials, double *sumsq,
-             double *r_keep, void *stream) {
+             double *r_keep, void *stream, void *event_after_last_pass) {
     int rc = check_op(op);
     if (rc) return rc;
     DGB_ARG(ctl && partials && sumsq);
@@ -434,6 +434,8 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
             }
             if (rc) return rc;
         }
+        if (it == max_iterations - 1 && event_after_last_pass != nullptr)       // u is final from here on
+            DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after_last_pass, (cudaStream_t)stream));
         if (check_residual) {
             rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, skip, stream);
             if (rc) return rc;

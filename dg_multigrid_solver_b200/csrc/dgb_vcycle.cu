@@ -11,8 +11,14 @@ namespace dgb {
 
 // *have_residual (optional, out): L.r holds rhs - A u of the returned u (the smoother's own last residual test)
 static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream, bool *have_residual = nullptr) {
+                  double *partials, double *sumsq, void *stream, bool *have_residual = nullptr,
+                  void *u_final_event = nullptr) {
     if (have_residual) *have_residual = false;
+    if (iterations <= 0 || L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG) {
+        // no in-smoother hook: the event is recorded by the caller after the smoother returns
+        if (u_final_event != nullptr && iterations <= 0)
+            DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)u_final_event, (cudaStream_t)stream));
+    }
     if (iterations <= 0) return 0;
     const size_t nbytes = sizeof(double) * (size_t)L.op.Ni * L.op.Nj * L.op.b;
     switch (L.smoother) {
@@ -22,7 +28,7 @@ static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, 
             return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream);
         }
         return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
-                        nullptr, stream);
+                        nullptr, stream, u_final_event);
     case DGB_SMOOTHER_BLOCK_JACOBI: {
         // relaxation.py:123-150: iteration 1 is Jacobi into a fresh buffer, then `u = u_new`
         // aliases the two, so the remaining iterations are in-place forward sweeps.
@@ -46,12 +52,17 @@ static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, 
 }
 
 static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream) {
+                  double *partials, double *sumsq, void *stream, bool top = false) {
     const dgb_level &L = lv[k];
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (k == 0)   // solver.py:201-204
-        return smooth(L, o, o.coarse_iterations, ctl + k, partials, sumsq, stream);
+    void *ev = top ? o.u_final_event : nullptr;
+    if (k == 0) {   // solver.py:201-204
+        rc = smooth(L, o, o.coarse_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
+        if (rc == 0 && ev != nullptr && L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG)
+            DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
+        return rc;
+    }
     const dgb_level &C = lv[k - 1];
     bool have_r = false;
     if ((rc = smooth(L, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r))) return rc;
@@ -62,7 +73,10 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.op.Ni * C.op.Nj * C.op.b, st));   // solver.py:171
     if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream))) return rc;
     if ((rc = dgb_prolong_add(C.transfer_kind, C.P, C.nc, C.nf, C.op.Ni, C.op.Nj, C.u, L.u, stream))) return rc;
-    return smooth(L, o, L.post_iterations, ctl + k, partials, sumsq, stream);
+    rc = smooth(L, o, L.post_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
+    if (rc == 0 && ev != nullptr && L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG && L.post_iterations > 0)
+        DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
+    return rc;
 }
 
 }  // namespace dgb
@@ -83,5 +97,5 @@ extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_
             }
         }
     }
-    return dgb::vcycle(h_levels, nlevels - 1, *h_opts, ctl, partials, sumsq, stream);
+    return dgb::vcycle(h_levels, nlevels - 1, *h_opts, ctl, partials, sumsq, stream, true);
 }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DGB_ABI_VERSION 3
+#define DGB_ABI_VERSION 4
 
 /* ---- status ------------------------------------------------------------------------- */
 int dgb_abi_version(void);
@@ -245,6 +245,10 @@ typedef struct dgb_vcycle_opts {
     int32_t check_residual;     /* 1 = reference semantics (early exit active)  */
     int32_t coarse_iterations;  /* 10 in the reference (solver.py:204)          */
     int32_t reserved;
+    void *u_final_event;        /* optional cudaEvent_t, recorded on `stream` right after the last kernel
+                                   that writes the finest level's u (the post-smoother's closing residual
+                                   test only reads it): a caller may copy u out on another stream from
+                                   there on.  NULL = not used.                  */
 } dgb_vcycle_opts;
 
 /* One V-cycle on the finest level: levels[n-1].u is updated in place from levels[n-1].rhs.

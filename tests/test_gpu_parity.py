@@ -414,3 +414,20 @@ def _chained_gs_checks(grid, Ni, Nj, L):
         assert np.abs(got[0] - ref).max() <= 1e-12 * scale, (direction, np.abs(got[0] - ref).max() / scale)
     # the mailbox is all-sentinel again after the passes
     assert bool((grid.d_mailbox.view(torch.int64) == -1).all())
+
+
+def test_vcycle_result_copied_out_on_second_stream():
+    """Solver.multigrid_V_cycle(..., out=pinned buffer): u leaves on a second stream from the event dgb_vcycle
+    records after the last sweep; same bits as the plain path."""
+    import torch
+    d = build(CASES["rect8_h24"])
+    fine = d.grids[-1]
+    k = len(d.grids)
+    u_plain = d.solver.multigrid_V_cycle(k=k, RHS=fine.RHS, u=np.zeros_like(fine.RHS))
+    out = torch.empty(fine.RHS.size, dtype=torch.float64).pin_memory()
+    rhs_h = torch.from_numpy(fine.RHS.copy()).pin_memory()
+    u_h = torch.zeros(fine.RHS.size, dtype=torch.float64).pin_memory()
+    for _ in range(3):
+        got = d.solver.multigrid_V_cycle(k=k, RHS=rhs_h, u=u_h, out=out)
+        assert got is out
+        assert np.array_equal(out.numpy(), u_plain)
