@@ -601,6 +601,54 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
     }
 }
 
+// ---- slabs: the c a chain pass leaves for the opposite direction lacks the terms of neighbours in ghost rows
+// (they are nobody's chain terms); after the halo exchange they are subtracted for the two edge rows:
+//     c_e -= Dinv_e A_e,ghost x_ghost        (one thread per scalar row of the ghost-adjacent element rows)
+template <int B>
+__global__ void __launch_bounds__(HelperCfg<B>::NT)
+k_gs_edge_helper(const double *__restrict__ data, const int32_t *__restrict__ indices,
+                 const int32_t *__restrict__ indptr, const double *__restrict__ dinv, const double *__restrict__ x,
+                 double *rec, Stencil S_, int dir, const int32_t *__restrict__ skip) {
+    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
+    if (skip != nullptr && *skip != 0) return;
+    __shared__ double s_t[EPB * B];
+    const int el = threadIdx.x / B, r = threadIdx.x - el * B;
+    const int Ni = S_.Ni;
+    const int nlo = S_.ja0 > 0 ? Ni : 0, nhi = S_.ja1 < S_.Nj ? Ni : 0;      // elements next to a ghost row
+    const int count = nlo + nhi;
+    const int ntiles = (count + EPB - 1) / EPB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int idx = tile * EPB + el;
+        int e = -1, eg = -1;
+        if (el < EPB && idx < count) {
+            const bool lo = idx < nlo;
+            const int i = lo ? idx : idx - nlo;
+            const int j = lo ? S_.ja0 : S_.ja1 - 1;
+            e = j * Ni + i;
+            eg = lo ? e - Ni : e + Ni;
+        }
+        // a slab of one active row has both ghost neighbours on the same element: handle lo then hi entries
+        if (e >= 0) {
+            double acc = 0.0;
+            for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj)
+                if (indices[jj] == eg) acc += row_dot<B>(data + ((size_t)jj * B + r) * B, x + (size_t)eg * B);
+            s_t[el * B + r] = acc;
+        }
+        __syncthreads();
+        if (e >= 0) {
+            const double *d = dinv + ((size_t)e * B + r) * B;
+            double tt = 0.0;
+#pragma unroll
+            for (int c = 0; c < B; ++c) tt = fma(d[c], s_t[el * B + c], tt);
+            const int j = e / Ni, i = e - j * Ni;
+            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r;
+            if (S_.ja1 - S_.ja0 == 1 && nlo && nhi) atomicAdd(mine, -tt);   // both ghost terms land on one entry
+            else *mine -= tt;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- records: { -Dinv_e A_e,row-predecessor | -Dinv_e A_e,previous-row | c | pad } at chain_loc(e) ----
 template <int B>
 __global__ void __launch_bounds__(256)
@@ -721,6 +769,8 @@ static int chain_launch_w(const double *rec, double *rec_other, double *x, doubl
                    : chain_launch_d<B, W, -1>(rec, rec_other, x, mbox, S_, skip, st);
 }
 
+bool chain_c_recurrence(int flags);
+
 // have_c: the previous pass of this smoother call ran in the opposite direction on the same rhs and x has
 // not changed since -- its chain left this pass's c in the record stream, the helper is not needed
 template <int B>
@@ -734,6 +784,13 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
     if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (have_c && !chain_c_recurrence(op->stencil)) {
+        const int edge = ((S_.ja0 > 0) + (S_.ja1 < S_.Nj)) * S_.Ni;
+        int ge = (edge + H::EPB - 1) / H::EPB;
+        if (ge > sm_count() * 8) ge = sm_count() * 8;
+        k_gs_edge_helper<B><<<ge, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, x, rec, S_, dir, skip);
+        DGB_LAUNCH_OK();
+    }
     if (!have_c && g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
         k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
                                                       S_, dir, skip, nullptr, nullptr);
@@ -782,7 +839,6 @@ int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir,
                   cudaStream_t st) {
     int rc = ensure_work(0);
     if (rc) return rc;
-    if (!chain_c_recurrence(op->stencil)) have_c = false;
     switch (op->b) {
     case 4: return chain_pass_t<4>(op, rhs, x, dir, have_c, skip, st);
     case 9: return chain_pass_t<9>(op, rhs, x, dir, have_c, skip, st);

@@ -602,6 +602,16 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     return lexicographic_pass(op, rhs, x, 1.0, direction, skip, st);
 }
 
+int dgb_block_gs_pass_seq(const dgb_operator *op, const double *rhs, double *x, int32_t direction,
+                          int32_t prev_direction, const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && rhs && x);
+    DGB_ARG(direction == 1 || direction == -1);
+    DGB_ARG(prev_direction == 0 || prev_direction == 1 || prev_direction == -1);
+    return lexicographic_pass(op, rhs, x, 1.0, direction, skip, (cudaStream_t)stream, prev_direction == -direction);
+}
+
 int dgb_block_gs_colour(const dgb_operator *op, const double *rhs, double *x, int32_t colour, int32_t shift,
                         const int32_t *skip, void *stream) {
     int rc = check_op(op);

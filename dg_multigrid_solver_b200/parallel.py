@@ -165,7 +165,9 @@ class DistributedSolver:
     def _ctl_ptr(self, k):
         return self.ctl.data_ptr() + 32 * k
 
-    def _gs_pass(self, k, rhs, u, direction, skip):
+    def _gs_pass(self, k, rhs, u, direction, skip, prev=0):
+        """One directional pass.  prev: direction of the previous pass of the same smoother call (0 = first):
+        an opposite previous pass lets the chained kernel skip its dependency-free launch."""
         import torch.distributed as dist
         g, op, st = self.grids[k], self.ops[k], self._st()
         if self.gs_mode == "redblack":
@@ -176,7 +178,7 @@ class DistributedSolver:
             return
         if self.gs_mode == "slab_lexicographic" or self.world == 1:
             self._halo(k, u)
-            _lib.call("dgb_block_gs_pass", op, rhs, u, direction, _lib.GS_LEXICOGRAPHIC, skip, st)
+            _lib.call("dgb_block_gs_pass_seq", op, rhs, u, direction, prev, skip, st)
             return
         # exact global lexicographic order: pipeline across ranks
         self._halo(k, u, upward=(direction < 0), downward=(direction > 0))     # old values of the slab ahead
@@ -189,7 +191,7 @@ class DistributedSolver:
         if not first:
             ghost = u[0:row] if direction > 0 else u[(n - 1) * row:n * row]
             dist.recv(ghost, src, group=self.group)
-        _lib.call("dgb_block_gs_pass", op, rhs, u, direction, _lib.GS_LEXICOGRAPHIC, skip, st)
+        _lib.call("dgb_block_gs_pass_seq", op, rhs, u, direction, prev, skip, st)
         if not last:
             edge = u[(n - 2) * row:(n - 1) * row] if direction > 0 else u[row:2 * row]
             dist.send(edge, dst, group=self.group)
@@ -199,7 +201,9 @@ class DistributedSolver:
         cf = g.coarsening_factor or 1
         return (self.part.j0 // cf - g.ghost_lo) & 1
 
-    def smooth(self, k, rhs, u, spec, iterations):
+    def smooth(self, k, rhs, u, spec, iterations, r_keep=None):
+        """One smoother call.  r_keep: every residual test also stores the residual vector there; returns True
+        when r_keep holds rhs - A u of the returned u (the caller then skips its own residual evaluation)."""
         name = spec.smoother
         direction = {"symmetric": 0, "forward": 1, "backward": -1}[spec.direction]
         g, st = self.grids[k], self._st()
@@ -207,17 +211,21 @@ class DistributedSolver:
         if name == "block_gauss_seidel_pyamg":
             skip = None
             if self.check:
-                self.residual_sumsq(k, rhs, u)
+                self.residual_sumsq(k, rhs, u, r=r_keep)
                 _lib.call("dgb_smoother_begin", self._ctl_ptr(k), self.sumsq, n_global, st)
                 skip = self._ctl_ptr(k) + 16                 # &ctl->skip
+            prev = 0
             for _ in range(int(iterations)):
                 if direction >= 0:
-                    self._gs_pass(k, rhs, u, +1, skip)
+                    self._gs_pass(k, rhs, u, +1, skip, prev)
+                    prev = +1
                 if direction <= 0:
-                    self._gs_pass(k, rhs, u, -1, skip)
+                    self._gs_pass(k, rhs, u, -1, skip, prev)
+                    prev = -1
                 if self.check:
-                    self.residual_sumsq(k, rhs, u, skip=skip)
+                    self.residual_sumsq(k, rhs, u, r=r_keep, skip=skip)
                     _lib.call("dgb_smoother_check", self._ctl_ptr(k), self.sumsq, n_global, st)
+            return bool(self.check and r_keep is not None and int(iterations) > 0)
         elif name == "block_jacobi":
             tmp = self.vec[k][2]
             self._halo(k, u)
@@ -237,8 +245,9 @@ class DistributedSolver:
         g, st = self.grids[k], self._st()
         rhs, u, r = self.vec[k]
         pre, post = self.sched[k]
-        self.smooth(k, rhs, u, pre, pre.iterations)
-        self.residual_sumsq(k, rhs, u, r=r)
+        # the pre-smoother's last residual test already evaluated the vector the restriction needs (solver.py:150)
+        if not self.smooth(k, rhs, u, pre, pre.iterations, r_keep=r):
+            self.residual_sumsq(k, rhs, u, r=r)
         kind = _lib.TRANSFER_H if self.types[k] == "geometric" else _lib.TRANSFER_P
         if k > 0:
             c = self.grids[k - 1]

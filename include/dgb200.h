@@ -156,6 +156,14 @@ int dgb_check_stencil(const int32_t *indices, const int32_t *indptr, int32_t Ni,
 int dgb_block_gs_pass(const dgb_operator *h_op, const double *rhs, double *x, int32_t direction,
                       int32_t mode, const int32_t *skip, void *stream);
 
+/* The same lexicographic pass as part of a sequence: prev_direction is the direction of the immediately
+ * preceding lexicographic pass on the SAME rhs, with x untouched since except for the ghost rows of a slab
+ * (0 = none / unknown).  When it is the opposite of `direction`, the chained kernel finds its right-hand
+ * sides where the previous pass left them and skips the dependency-free launch (slabs: only the ghost-row
+ * terms are refreshed). */
+int dgb_block_gs_pass_seq(const dgb_operator *h_op, const double *rhs, double *x, int32_t direction,
+                          int32_t prev_direction, const int32_t *skip, void *stream);
+
 /* One colour class of the 2-colour sweep: rows with ((i + j + shift) & 1) == colour are relaxed in place.
  * `shift` carries the global row parity of a slab so that all ranks colour the global grid alike; the
  * caller exchanges halos between the two colours. */
