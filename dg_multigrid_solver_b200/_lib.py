@@ -58,6 +58,7 @@ GS_LEXICOGRAPHIC, GS_REDBLACK = 0, 1
 TRANSFER_P, TRANSFER_H = 1, 2
 SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_seidel": 2}
 FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV, FLAG_GHOST_LO, FLAG_GHOST_HI = 1, 2, 4, 8, 16
+UNSUPPORTED = 100        # DGB_UNSUPPORTED
 
 # name -> (restype, argtypes); every symbol include/dgb200.h declares
 OP = ctypes.POINTER(Operator)
@@ -79,6 +80,7 @@ SIGNATURES = {
     "dgb_check_stencil": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_pass": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_pass_seq": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_gs_entry_residual": (c_i32, [OP, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_block_gs_colour": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_relax_sweep": (c_i32, [OP, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),

@@ -563,7 +563,9 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             double acc = 0.0, acc_chain = 0.0;
             for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
                 const int col = indices[jj];
-                const bool chain_part = col == e || col == e_row || col == e_up;
+                // RES (entry of a smoother call): neighbours in ghost rows are left to the edge kernel of the pass
+                // that follows (dgb_block_gs_pass_seq), which sees the halo values of that moment
+                const bool chain_part = col == e || col == e_row || col == e_up || (RES && !S_.active(col / Ni));
                 if (!RES && chain_part) continue;
                 const double tt = row_dot<B>(data + ((size_t)jj * B + r) * B, x + (size_t)col * B);
                 if (chain_part) acc_chain += tt;

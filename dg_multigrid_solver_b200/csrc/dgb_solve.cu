@@ -612,6 +612,23 @@ int dgb_block_gs_pass_seq(const dgb_operator *op, const double *rhs, double *x, 
     return lexicographic_pass(op, rhs, x, 1.0, direction, skip, (cudaStream_t)stream, prev_direction == -direction);
 }
 
+int dgb_block_gs_entry_residual(const dgb_operator *op, const double *rhs, const double *x, int32_t first_direction,
+                                double *r, double *partials, double *sumsq, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && rhs && x && partials && sumsq);
+    DGB_ARG(first_direction == 1 || first_direction == -1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(use_stream(op) && op->gs_chain != nullptr && op->gs_mailbox != nullptr && chain_supported(op->b, op->stencil)))
+        return DGB_UNSUPPORTED;
+    int grid = 1;
+    rc = gs_chain_helper_residual(op, rhs, x, first_direction, r, partials, &grid, st);
+    if (rc) return rc;
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, nullptr);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
 int dgb_block_gs_colour(const dgb_operator *op, const double *rhs, double *x, int32_t colour, int32_t shift,
                         const int32_t *skip, void *stream) {
     int rc = check_op(op);

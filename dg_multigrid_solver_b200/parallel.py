@@ -153,13 +153,25 @@ class DistributedSolver:
         g = self.grids[k]
         exchange_halo(v, g.Ni, g.b, g.ghost_lo, g.ghost_hi, self.rank, self.world, self.group, upward, downward)
 
-    def residual_sumsq(self, k, rhs, u, r=None, skip=None):
-        """Global sum of squares of rhs - A u over owned rows (device scalar self.sumsq)."""
+    def residual_sumsq(self, k, rhs, u, r=None, skip=None, first_direction=0):
+        """Global sum of squares of rhs - A u over owned rows (device scalar self.sumsq).
+        first_direction != 0: this is the entry residual of a lexicographic smoother call whose first pass runs in
+        that direction -- it shares the launch of that pass's dependency-free part; returns True when it did."""
         import torch.distributed as dist
         self._halo(k, u)
-        _lib.call("dgb_bsr_residual", self.ops[k], rhs, u, r, self.partials, self.sumsq, skip, self._st())
+        fused = False
+        if first_direction != 0 and skip is None:
+            L = _lib.load()
+            rc = L.dgb_block_gs_entry_residual(ctypes.byref(self.ops[k]), _lib.ptr(rhs), _lib.ptr(u), first_direction,
+                                               _lib.ptr(r), _lib.ptr(self.partials), _lib.ptr(self.sumsq), self._st())
+            if rc != _lib.UNSUPPORTED:
+                _lib.check(rc, "dgb_block_gs_entry_residual")
+                fused = True
+        if not fused:
+            _lib.call("dgb_bsr_residual", self.ops[k], rhs, u, r, self.partials, self.sumsq, skip, self._st())
         if self.world > 1:
             dist.all_reduce(self.sumsq, group=self.group)
+        self._entry_fused = fused
         return self.sumsq
 
     def _ctl_ptr(self, k):
@@ -210,11 +222,15 @@ class DistributedSolver:
         n_global = self.n_owned[k] * self.world
         if name == "block_gauss_seidel_pyamg":
             skip = None
+            prev = 0
             if self.check:
-                self.residual_sumsq(k, rhs, u, r=r_keep)
+                first = +1 if direction >= 0 else -1
+                lexi = self.gs_mode != "redblack" and int(iterations) > 0
+                self.residual_sumsq(k, rhs, u, r=r_keep, first_direction=first if lexi else 0)
+                if self._entry_fused:
+                    prev = -first                             # the first pass finds its right-hand sides in place
                 _lib.call("dgb_smoother_begin", self._ctl_ptr(k), self.sumsq, n_global, st)
                 skip = self._ctl_ptr(k) + 16                 # &ctl->skip
-            prev = 0
             for _ in range(int(iterations)):
                 if direction >= 0:
                     self._gs_pass(k, rhs, u, +1, skip, prev)

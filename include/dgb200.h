@@ -164,6 +164,16 @@ int dgb_block_gs_pass(const dgb_operator *h_op, const double *rhs, double *x, in
 int dgb_block_gs_pass_seq(const dgb_operator *h_op, const double *rhs, double *x, int32_t direction,
                           int32_t prev_direction, const int32_t *skip, void *stream);
 
+/* Entry residual of a smoother call fused with the dependency-free part of its first lexicographic pass
+ * (direction first_direction): r = rhs - A x (r may be NULL), *sumsq = sum r^2, and the chained kernel's
+ * right-hand sides for that pass -- follow with dgb_block_gs_pass_seq(..., direction = first_direction,
+ * prev_direction = -first_direction).  Returns DGB_UNSUPPORTED (nothing launched) when the operator has no
+ * chained kernel; the caller then uses dgb_bsr_residual. */
+#define DGB_UNSUPPORTED 100
+int dgb_block_gs_entry_residual(const dgb_operator *h_op, const double *rhs, const double *x,
+                                int32_t first_direction, double *r, double *partials, double *sumsq,
+                                void *stream);
+
 /* One colour class of the 2-colour sweep: rows with ((i + j + shift) & 1) == colour are relaxed in place.
  * `shift` carries the global row parity of a slab so that all ranks colour the global grid alike; the
  * caller exchanges halos between the two colours. */
