@@ -36,20 +36,20 @@ extern int g_gs_variant;
 template <int B>
 struct ChainCfg {
     static constexpr int B2 = B * B;
-    static constexpr int P = B == 9 ? 3 : 1;                          // lanes per scalar row (each takes B/P columns)
+    static constexpr int P = B == 9 ? 3 : B == 16 ? 2 : 1;            // lanes per scalar row (each takes B/P columns)
     static constexpr int CW = B / P;                                  // matrix columns per lane
     static constexpr int LPR = B * P;                                 // lanes per element row
     static constexpr int R = 32 / LPR;                                // element rows per warp
     static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
-    static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 2 : 1;           // steps per chunk (one bulk copy)
-    static constexpr int NS = B == 9 ? 2 : 3;                         // bulk-copy stages
+    static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 4 : 1;           // steps per chunk (one bulk copy)
+    static constexpr int NS = (B == 9 || B == 16) ? 2 : 3;            // bulk-copy stages
     static constexpr int RING = B <= 9 ? 32 : 16;                     // columns per band hand-over ring
     static constexpr int RINGR = CH < 2 ? 2 : CH;                     // steps per row ring (rows of one warp)
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
-    static constexpr int WDEF = B == 9 ? 8 : (B <= 4 || B == 16) ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
+    static constexpr int WDEF = B == 9 ? 8 : B == 16 ? 5 : B <= 4 ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
     static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
     static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
@@ -113,7 +113,7 @@ struct ChainRow {
         constexpr int B2 = B * B;
         c = lds1(rc);
         d = lds1(rc + B * 8);
-        if (P == 1 && B % 2 == 0) {
+        if (CW % 2 == 0 && B % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < CW; k += 2) {
                 const double2 m0 = lds2(rm + k * 8), m1 = lds2(rm + (B2 + k) * 8);
@@ -692,7 +692,7 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
 // host side
 // block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25
 // (dgb_set_kernel_path(300 + mask); the default follows the measurements in profiles/)
-int g_chain_mask = 11;
+int g_chain_mask = 15;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : 0;
