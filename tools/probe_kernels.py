@@ -6,7 +6,7 @@ import os
 import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "oracle")]
+sys.path[:0] = [REPO]
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
