@@ -538,7 +538,7 @@ struct HelperCfg {
 // RES: also evaluate the full residual r = rhs - A x (optionally stored) and its sum of squares (one partial per
 // CTA) -- the smoother's entry residual test (dgfem/relaxation.py:202) shares the block reads of the first pass.
 template <int B, bool RES>
-__global__ void __launch_bounds__(HelperCfg<B>::NT)
+__global__ void __launch_bounds__(HelperCfg<B>::NT, RES ? 6 : 8)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
             double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
@@ -565,7 +565,7 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
                 const int col = indices[jj];
                 // RES (entry of a smoother call): neighbours in ghost rows are left to the edge kernel of the pass
                 // that follows (dgb_block_gs_pass_seq), which sees the halo values of that moment
-                const bool chain_part = col == e || col == e_row || col == e_up || (RES && !S_.active(col / Ni));
+                const bool chain_part = col == e || col == e_row || col == e_up || (RES && (col < first || col >= first + count));
                 if (!RES && chain_part) continue;
                 const double tt = row_dot<B>(data + ((size_t)jj * B + r) * B, x + (size_t)col * B);
                 if (chain_part) acc_chain += tt;
@@ -814,7 +814,7 @@ static int helper_residual_t(const dgb_operator *op, const double *rhs, const do
     double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
-    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (grid > sm_count() * 6) grid = sm_count() * 6;       // one wave at the occupancy __launch_bounds__ asks for
     if (grid > kMaxPartials) grid = kMaxPartials;
     k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
                                                  dir, nullptr, r, partials);
