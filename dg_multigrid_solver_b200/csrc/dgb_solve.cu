@@ -138,9 +138,20 @@ k_sumsq(const double *__restrict__ v, int64_t n, double *partials) {
     if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
-static int rows_grid(int count, int epb) {
+// CTAs per SM the kernel can actually keep resident (registers): the grid is ONE wave of persistent CTAs
+template <int B, int MODE>
+static int rows_occupancy() {
+    static int occ = 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<B, MODE>, RowCfg<B>::NT, 0) != cudaSuccess || occ < 1)
+            occ = 1;
+        if (occ > 8) occ = 8;
+    }
+    return occ;
+}
+static int rows_grid(int count, int epb, int occ = 8) {
     const int ntiles = (count + epb - 1) / epb;
-    int g = sm_count() * 8;
+    int g = sm_count() * occ;
     if (g > kMaxPartials) g = kMaxPartials;
     if (g > ntiles) g = ntiles;
     return g < 1 ? 1 : g;
@@ -474,7 +485,7 @@ int dgb_bsr_apply(const dgb_operator *op, const double *x, double *y, void *stre
         return stream_launch(S_APPLY, op->b, op->data, op->indices, op->indptr, N, op->Ni, nullptr, x, y, nullptr,
                              1.0, -1, nullptr, st, nullptr);
     Sel sel{0, 0, N, 1, 0, N};
-    DGB_DISPATCH_B(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+    DGB_DISPATCH_B(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_APPLY>()), RowCfg<B>::NT, 0, st>>>(
                               op->data, op->indices, op->indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
     DGB_LAUNCH_OK();
     return 0;
@@ -494,7 +505,7 @@ int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x,
         if (rc) return rc;
     } else {
         Sel sel{0, 0, N, 1, 0, N};
-        DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB);
+        DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
                        k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
                            op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
         DGB_LAUNCH_OK();
@@ -543,7 +554,7 @@ int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_
 static int relax_launch(const dgb_operator *op, const double *rhs, const double *x_in, double *x_out,
                         double omega, Sel sel, const int32_t *skip, cudaStream_t st) {
     if (sel.count <= 0) return 0;
-    DGB_DISPATCH_B(op->b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB), RowCfg<B>::NT, 0, st>>>(
+    DGB_DISPATCH_B(op->b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RELAX>()), RowCfg<B>::NT, 0, st>>>(
                               op->data, op->indices, op->indptr, op->dinv, rhs, x_in, x_out, nullptr, omega, sel, skip));
     DGB_LAUNCH_OK();
     return 0;
