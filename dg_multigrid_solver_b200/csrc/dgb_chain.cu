@@ -41,6 +41,13 @@ struct ChainCfg {
     static constexpr int LPR = B * P;                                 // lanes per element row
     static constexpr int R = 32 / LPR;                                // element rows per warp
     static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
+    // P > 1: the two blocks of a record are stored lane-major, MV doubles at a time, so that the lanes of a row
+    // read consecutive shared-memory words (no bank conflicts): entry (r, c) of a block sits at mat_offset(r, c)
+    static constexpr int MV = (P > 1 && CW % 2 == 0) ? 2 : 1;
+    __host__ __device__ static constexpr int mat_offset(int r, int c) {
+        return P == 1 ? r * B + c
+                      : ((c % CW) / MV) * (LPR * MV) + (r * P + c / CW) * MV + (c % CW) % MV;
+    }
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
     static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 4 : 1;           // steps per chunk (one bulk copy)
     static constexpr int NS = (B == 9 || B == 16) ? 2 : 3;            // bulk-copy stages
@@ -113,7 +120,23 @@ struct ChainRow {
         constexpr int B2 = B * B;
         c = lds1(rc);
         d = lds1(rc + B * 8);
-        if (CW % 2 == 0 && B % 2 == 0) {
+        if (P > 1) {                 // lane-major layout: my k-th entry is LPR * MV doubles after my (k - MV)-th
+            constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
+            if (MV == 2) {
+#pragma unroll
+                for (int k = 0; k < CW; k += 2) {
+                    const double2 m0 = lds2(rm + (k / 2) * LS * 8), m1 = lds2(rm + (B2 + (k / 2) * LS) * 8);
+                    ml[k] = m0.x; ml[k + 1 < CW ? k + 1 : k] = m0.y;
+                    mu[k] = m1.x; mu[k + 1 < CW ? k + 1 : k] = m1.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < CW; ++k) {
+                    ml[k] = lds1(rm + k * LS * 8);
+                    mu[k] = lds1(rm + (B2 + k * LS) * 8);
+                }
+            }
+        } else if (B % 2 == 0) {
 #pragma unroll
             for (int k = 0; k < CW; k += 2) {
                 const double2 m0 = lds2(rm + k * 8), m1 = lds2(rm + (B2 + k) * 8);
@@ -373,7 +396,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
                                          : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
     uint32_t sen_w = (fin && first_row) ? in_b + 8 * r : scr + 8 * lane;         // row 0 hands the incoming slot back
-    uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + r * B + part * CW) * 8);   // my matrix entries, stage 0 step 0
+    uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + C::mat_offset(r, part * CW)) * 8);   // my first matrix entry, stage 0 step 0
     uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
     uint32_t own_w = fin ? own_b + 8 * r : scr + 8 * lane;
     const uint32_t first_mask = (fin && first_row) ? 0xffffffffu : 0u;
@@ -684,7 +707,7 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
             }
         }
         if (S_.active(j))
-            rec[((size_t)(slot >> 1) * chain_dir_records<B>(S_) + (size_t)chain_loc<B>(S_, dir, i, j)) * REC + (slot & 1) * B2 + rc] = v;
+            rec[((size_t)(slot >> 1) * chain_dir_records<B>(S_) + (size_t)chain_loc<B>(S_, dir, i, j)) * REC + (slot & 1) * B2 + ChainCfg<B>::mat_offset(r, c)] = v;
     }
 }
 
