@@ -41,12 +41,11 @@ struct ChainCfg {
     static constexpr int LPR = B * P;                                 // lanes per element row
     static constexpr int R = 32 / LPR;                                // element rows per warp
     static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
-    // P > 1: the two blocks of a record are stored lane-major, MV doubles at a time, so that the lanes of a row
+    // the two blocks of a record are stored lane-major, MV doubles at a time, so that the lanes of an element row
     // read consecutive shared-memory words (no bank conflicts): entry (r, c) of a block sits at mat_offset(r, c)
-    static constexpr int MV = (P > 1 && CW % 2 == 0) ? 2 : 1;
+    static constexpr int MV = (CW % 2 == 0) ? 2 : 1;
     __host__ __device__ static constexpr int mat_offset(int r, int c) {
-        return P == 1 ? r * B + c
-                      : ((c % CW) / MV) * (LPR * MV) + (r * P + c / CW) * MV + (c % CW) % MV;
+        return ((c % CW) / MV) * (LPR * MV) + (r * P + c / CW) * MV + (c % CW) % MV;
     }
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
     static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 4 : 1;           // steps per chunk (one bulk copy)
@@ -120,34 +119,20 @@ struct ChainRow {
         constexpr int B2 = B * B;
         c = lds1(rc);
         d = lds1(rc + B * 8);
-        if (P > 1) {                 // lane-major layout: my k-th entry is LPR * MV doubles after my (k - MV)-th
-            constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
-            if (MV == 2) {
-#pragma unroll
-                for (int k = 0; k < CW; k += 2) {
-                    const double2 m0 = lds2(rm + (k / 2) * LS * 8), m1 = lds2(rm + (B2 + (k / 2) * LS) * 8);
-                    ml[k] = m0.x; ml[k + 1 < CW ? k + 1 : k] = m0.y;
-                    mu[k] = m1.x; mu[k + 1 < CW ? k + 1 : k] = m1.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < CW; ++k) {
-                    ml[k] = lds1(rm + k * LS * 8);
-                    mu[k] = lds1(rm + (B2 + k * LS) * 8);
-                }
-            }
-        } else if (B % 2 == 0) {
+        // lane-major layout: my k-th entry is LPR * MV doubles after my (k - MV)-th
+        constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
+        if (MV == 2) {
 #pragma unroll
             for (int k = 0; k < CW; k += 2) {
-                const double2 m0 = lds2(rm + k * 8), m1 = lds2(rm + (B2 + k) * 8);
+                const double2 m0 = lds2(rm + (k / 2) * LS * 8), m1 = lds2(rm + (B2 + (k / 2) * LS) * 8);
                 ml[k] = m0.x; ml[k + 1 < CW ? k + 1 : k] = m0.y;
                 mu[k] = m1.x; mu[k + 1 < CW ? k + 1 : k] = m1.y;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < CW; ++k) {
-                ml[k] = lds1(rm + k * 8);
-                mu[k] = lds1(rm + (B2 + k) * 8);
+                ml[k] = lds1(rm + k * LS * 8);
+                mu[k] = lds1(rm + (B2 + k * LS) * 8);
             }
         }
     }
