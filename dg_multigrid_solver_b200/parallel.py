@@ -62,6 +62,44 @@ def slab_nodes(xn, yn, Pg, part, halo):
     return np.ascontiguousarray(xn[r0:r1]), np.ascontiguousarray(yn[r0:r1]), lo, hi
 
 
+def _host_staged(group=None):
+    """True when the process group cannot move device tensors itself (gloo): the slab code then stages its
+    messages through host memory.  Used by the tests to run two ranks on ONE GPU; production runs use NCCL."""
+    import torch.distributed as dist
+    return dist.get_backend(group) == "gloo"
+
+
+def _p2p(sends, recvs, group=None):
+    """sends: [(device tensor, dst)], recvs: [(device tensor, src)] -- one batch of point-to-point messages."""
+    import torch.distributed as dist
+    if not sends and not recvs:
+        return
+    if _host_staged(group):
+        hs = [(t.cpu(), dst) for t, dst in sends]
+        hr = [(t.new_empty(t.shape, device="cpu"), src, t) for t, src in recvs]
+        reqs = [dist.isend(h, dst, group=group) for h, dst in hs] + [dist.irecv(h, src, group=group) for h, src, _ in hr]
+        for q in reqs:
+            q.wait()
+        for h, _, t in hr:
+            t.copy_(h)
+        return
+    ops = [dist.P2POp(dist.isend, t, dst, group) for t, dst in sends] + \
+          [dist.P2POp(dist.irecv, t, src, group) for t, src in recvs]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def _all_reduce(t, group=None, op=None):
+    import torch.distributed as dist
+    op = op or dist.ReduceOp.SUM
+    if _host_staged(group):
+        h = t.cpu()
+        dist.all_reduce(h, op=op, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=op, group=group)
+
+
 def exchange_halo(vec, Ni, b, ghost_lo, ghost_hi, rank, world, group=None, upward=True, downward=True):
     """Fill the ghost rows of `vec` ([Nj_ext*Ni*b], ghost rows first/last) from the neighbour slabs.
     upward:   my last owned row  -> rank+1's lower ghost row (and I receive rank-1's into my lower ghost)
@@ -69,26 +107,29 @@ def exchange_halo(vec, Ni, b, ghost_lo, ghost_hi, rank, world, group=None, upwar
     import torch.distributed as dist
     row = Ni * b
     n = vec.numel() // row
-    ops = []
+    sends, recvs = [], []
     if upward:
         if ghost_hi:
-            ops.append(dist.P2POp(dist.isend, vec[(n - 2) * row:(n - 1) * row], rank + 1, group))
+            sends.append((vec[(n - 2) * row:(n - 1) * row], rank + 1))
         if ghost_lo:
-            ops.append(dist.P2POp(dist.irecv, vec[0:row], rank - 1, group))
+            recvs.append((vec[0:row], rank - 1))
     if downward:
         if ghost_lo:
-            ops.append(dist.P2POp(dist.isend, vec[row:2 * row], rank - 1, group))
+            sends.append((vec[row:2 * row], rank - 1))
         if ghost_hi:
-            ops.append(dist.P2POp(dist.irecv, vec[(n - 1) * row:n * row], rank + 1, group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            recvs.append((vec[(n - 1) * row:n * row], rank + 1))
+    _p2p(sends, recvs, group)
 
 
 def gather_rows(local_owned, world, rank, group=None):
     """Concatenate the ranks' owned chunks (equal sizes) on rank 0 -> global vector in element order."""
     import torch
     import torch.distributed as dist
+    if _host_staged(group):
+        h = local_owned.cpu()
+        out = [torch.empty_like(h) for _ in range(world)] if rank == 0 else None
+        dist.gather(h, out, dst=0, group=group)
+        return torch.cat(out).to(local_owned.device) if rank == 0 else None
     out = [torch.empty_like(local_owned) for _ in range(world)] if rank == 0 else None
     dist.gather(local_owned, out, dst=0, group=group)
     return torch.cat(out) if rank == 0 else None
@@ -97,6 +138,11 @@ def gather_rows(local_owned, world, rank, group=None):
 def scatter_rows(global_vec, like, world, rank, group=None):
     import torch
     import torch.distributed as dist
+    if _host_staged(group):
+        out = torch.empty(like.shape, dtype=like.dtype, device="cpu")
+        chunks = [c.contiguous() for c in global_vec.cpu().chunk(world)] if rank == 0 else None
+        dist.scatter(out, chunks, src=0, group=group)
+        return out.to(like.device)
     out = torch.empty_like(like)
     chunks = list(global_vec.chunk(world)) if rank == 0 else None
     dist.scatter(out, chunks, src=0, group=group)
@@ -170,7 +216,7 @@ class DistributedSolver:
         if not fused:
             _lib.call("dgb_bsr_residual", self.ops[k], rhs, u, r, self.partials, self.sumsq, skip, self._st())
         if self.world > 1:
-            dist.all_reduce(self.sumsq, group=self.group)
+            _all_reduce(self.sumsq, self.group)
         self._entry_fused = fused
         return self.sumsq
 
@@ -202,11 +248,11 @@ class DistributedSolver:
         dst = self.rank + 1 if direction > 0 else self.rank - 1
         if not first:
             ghost = u[0:row] if direction > 0 else u[(n - 1) * row:n * row]
-            dist.recv(ghost, src, group=self.group)
+            _p2p([], [(ghost, src)], self.group)
         _lib.call("dgb_block_gs_pass_seq", op, rhs, u, direction, prev, skip, st)
         if not last:
             edge = u[(n - 2) * row:(n - 1) * row] if direction > 0 else u[row:2 * row]
-            dist.send(edge, dst, group=self.group)
+            _p2p([(edge, dst)], [], self.group)
 
     def _colour_shift(self, g):
         """Global colour (i+j_global)&1 from the local row index: j_global = j_local - ghost_lo + j0/cf."""

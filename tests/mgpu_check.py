@@ -20,8 +20,14 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if os.environ.get("DGB_MGPU_ONE_DEVICE") == "1":
+        # all ranks share cuda:0 and talk through gloo + host staging (parallel._host_staged): lets the round-end
+        # single-GPU test box exercise the slab code with ghost rows
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from dg_multigrid_solver_b200.dgfem import DGFEM
     from dg_multigrid_solver_b200.grid import Geometry
     from dg_multigrid_solver_b200.parallel import build_distributed
@@ -53,7 +59,7 @@ def main():
             print(msg, flush=True)
         del ds
         torch.cuda.empty_cache()
-    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    flag = torch.tensor([1.0 if ok else 0.0], device="cpu" if dist.get_backend() == "gloo" else "cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     if rank == 0:
