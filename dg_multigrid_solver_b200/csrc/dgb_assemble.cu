@@ -157,13 +157,16 @@ struct FaceInfo {
     int nbr;       // neighbour element or -1
 };
 
+// BT, QT: block size and quadrature points per direction as compile-time constants (0 = read them from the
+// tables): all the index arithmetic of the item loops then folds into multiplications
+template <int BT, int QT>
 __global__ void __launch_bounds__(256)
 k_assemble_poisson(TabView T, const double *__restrict__ vol, const double *__restrict__ face,
                    const double *__restrict__ area, Stencil S, double nu, double sigma, int use_minv,
                    int32_t *__restrict__ indptr, int32_t *__restrict__ indices,
                    double *__restrict__ data, double *__restrict__ minv_out) {
     extern __shared__ double sm[];
-    const int b = T.b, nq = T.nq, nq1 = T.nq1, bb = b * b;
+    const int b = BT > 0 ? BT : T.b, nq1 = QT > 0 ? QT : T.nq1, nq = nq1 * nq1, bb = b * b;
     double *blk = sm;                       // [6][bb]
     double *Dx = blk + 6 * bb;              // [nq][b]
     double *Dy = Dx + nq * b;               // [nq][b]
@@ -242,14 +245,25 @@ k_assemble_poisson(TabView T, const double *__restrict__ vol, const double *__re
             dnN[t] = v;
         }
         __syncthreads();
-        // block entries: item = (slot s in 0..5, k, l); slot 5 = mass matrix
-        for (int t = tid; t < 6 * bb; t += nt) {
+        // the mass matrix first (slot 5) ...
+        for (int kl = tid; kl < bb; kl += nt) {
+            const int k = kl / b, l = kl - k * b;
+            double acc = 0.0;
+            for (int q = 0; q < nq; ++q) acc = fma(T.V[q * b + k] * wJ[q], T.V[q * b + l], acc);
+            blk[5 * bb + kl] = acc;
+        }
+        __syncthreads();
+        // ... then warp 0 inverts it in place while the other warps compute the five operator blocks
+        // (item = (slot s in 0..4, k, l))
+        if (tid < 32) {
+            warp_invert(blk + 5 * bb, s_piv, b, tid);
+        }
+        const int first = nt > 32 ? 32 : 0, nw = nt > 32 ? nt - 32 : nt;
+        for (int t = tid - first; t >= 0 && t < 5 * bb; t += nw) {
             const int s = t / bb, kl = t - s * bb;
             const int k = kl / b, l = kl - k * b;
             double acc = 0.0;
-            if (s == 5) {
-                for (int q = 0; q < nq; ++q) acc = fma(T.V[q * b + k] * wJ[q], T.V[q * b + l], acc);
-            } else if (s == 0) {
+            if (s == 0) {
                 double kv = 0.0;
                 for (int q = 0; q < nq; ++q)
                     kv = fma(wJ[q], Dx[q * b + k] * Dx[q * b + l] + Dy[q * b + k] * Dy[q * b + l], kv);
@@ -289,11 +303,6 @@ k_assemble_poisson(TabView T, const double *__restrict__ vol, const double *__re
                 }
             }
             blk[t] = acc;
-        }
-        __syncthreads();
-        // M^-1 by warp 0 (in place in blk[5])
-        if (tid < 32) {
-            warp_invert(blk + 5 * bb, s_piv, b, tid);
         }
         __syncthreads();
         const double *Mi = blk + 5 * bb;
@@ -473,12 +482,26 @@ int dgb_assemble_poisson(const dgb_tables *t, const double *vol, const double *f
     const size_t bb = (size_t)T.b * T.b;
     const size_t smem = sizeof(double) * (6 * bb + 2 * (size_t)T.nq * T.b + T.nq + 4 * T.nq1 +
                                           2 * 4 * (size_t)T.nq1 * T.b);
-    DGB_CUDA_OK(cudaFuncSetAttribute(k_assemble_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t g = (int64_t)Ni * Nj;
     if (g > sm_count() * 16) g = sm_count() * 16;
     const int nt = T.b >= 16 ? 256 : 128;
-    k_assemble_poisson<<<(int)g, nt, smem, st>>>(T, vol, face, area, S, nu, sigma,
-                                                (flags & DGB_FLAG_MINV) ? 1 : 0, indptr, indices, data, minv);
+    const int um = (flags & DGB_FLAG_MINV) ? 1 : 0;
+#define DGB_ASM_LAUNCH(BT, QT)                                                                                  \
+    do {                                                                                                        \
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_assemble_poisson<BT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                           \
+        k_assemble_poisson<BT, QT><<<(int)g, nt, smem, st>>>(T, vol, face, area, S, nu, sigma, um, indptr,     \
+                                                             indices, data, minv);                              \
+    } while (0)
+    // (p+1)^2 blocks with the reference's N_int = 3p/2 + 1 points per direction (grid.py:107); anything else
+    // (e.g. another integration-order factor) takes the runtime-sized instance
+    if (T.b == 4 && T.nq1 == 2) DGB_ASM_LAUNCH(4, 2);
+    else if (T.b == 9 && T.nq1 == 4) DGB_ASM_LAUNCH(9, 4);
+    else if (T.b == 16 && T.nq1 == 5) DGB_ASM_LAUNCH(16, 5);
+    else if (T.b == 25 && T.nq1 == 7) DGB_ASM_LAUNCH(25, 7);
+    else if (T.b == 36 && T.nq1 == 8) DGB_ASM_LAUNCH(36, 8);
+    else DGB_ASM_LAUNCH(0, 0);
+#undef DGB_ASM_LAUNCH
     DGB_LAUNCH_OK();
     return 0;
 }

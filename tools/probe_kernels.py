@@ -44,6 +44,15 @@ def main():
     geo = Geometry(None, s, nodes=nodes(ni, nj, Pg))
     g = Grid(geo, ["u"]).initialize({"u": p}, None)
     DiscreteSystem(s).problem.assemble(g)
+    asm_ms = None
+    if os.environ.get("DGB_PROBE_ASSEMBLY"):            # re-run the operator assembly kernel alone, device-timed
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.call("dgb_assemble_poisson", g._h_tables, g.d_vol, g.d_face, g.d_area, g.Ni, g.Nj, 1.0, float(g.sigma),
+                  g.flags, g.d_indptr, g.d_indices, g.d_data, g.d_minv, _lib.stream_ptr())
+        ev1.record(); torch.cuda.synchronize()
+        asm_ms = ev0.elapsed_time(ev1)
     g.release_geometry()
     L = _lib.load()
     st = _lib.stream_ptr()
@@ -64,6 +73,9 @@ def main():
         c.record(); torch.cuda.synchronize()
         return a.elapsed_time(c) / reps
     out = {"Ni": ni, "Nj": nj, "p": p, "b": b, "GB": {k: v / 1e9 for k, v in ab.items()}}
+    if asm_ms is not None:
+        out["assemble_poisson_ms"] = asm_ms
+        out["assemble_elements_per_s"] = N / (asm_ms * 1e-3)
     calls = {
         "apply": (lambda: _lib.call("dgb_bsr_apply", op, x, y, st), ab["apply"]),
         "residual": (lambda: _lib.call("dgb_bsr_residual", op, g.d_rhs, x, None, part, ss, None, st), ab["residual"]),
