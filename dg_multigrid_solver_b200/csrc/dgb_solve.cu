@@ -55,12 +55,34 @@ enum { MODE_APPLY = 0, MODE_RESIDUAL = 1, MODE_RELAX = 2 };
 
 template <int B>
 struct RowCfg {
-    static constexpr int EPB = (256 / B) > 0 ? (256 / B) : 1;  // elements per CTA
-    static constexpr int NT = ((EPB * B + 31) / 32) * 32;      // threads per CTA
+    // lanes per scalar row: rows of 128 bytes and more are shared by two adjacent lanes that take alternate
+    // 16-byte pieces, so one warp-wide load touches half as many cache lines (the L1 tag stage bounds these)
+    static constexpr int LP = (B >= 16 && B % 2 == 0) ? 2 : 1;
+    static constexpr int EPB = (256 / (B * LP)) > 0 ? (256 / (B * LP)) : 1;  // elements per CTA
+    static constexpr int NT = ((EPB * B * LP + 31) / 32) * 32;               // threads per CTA
 };
 
-// One thread per scalar row (element e, row r).  Blocks are read straight from global
-// memory (row-major 8*B-byte rows per thread; the L1 serves the neighbouring columns).
+// my share of sum_c a[c] x[c]: all of it (LP == 1, scipy's order), or the 16-byte pieces h, h+2, ... (LP == 2)
+template <int B, int LP>
+__device__ __forceinline__ double row_dot_part(const double *__restrict__ a, const double *__restrict__ x, int h) {
+    if (LP == 1) return row_dot<B>(a, x);
+    const double2 *a2 = reinterpret_cast<const double2 *>(a);
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    double t = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < (B / 2 + 1) / 2; ++kk) {
+        const int k = 2 * kk + h;
+        if (k < B / 2) {
+            const double2 v = a2[k], w = x2[k];
+            t = fma(v.x, w.x, t);
+            t = fma(v.y, w.y, t);
+        }
+    }
+    return t;
+}
+
+// One thread (LP == 1) or two adjacent lanes (LP == 2) per scalar row (element e, row r).  Blocks are read
+// straight from global memory in aligned 16-byte pieces (the L1 serves the neighbouring columns).
 template <int B, int MODE>
 __global__ void __launch_bounds__(RowCfg<B>::NT)
 k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
@@ -69,12 +91,15 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
        double omega, Sel sel, const int32_t *__restrict__ skip) {
     constexpr int EPB = RowCfg<B>::EPB;
     constexpr int NT = RowCfg<B>::NT;
+    constexpr int LP = RowCfg<B>::LP;
     if (skip != nullptr && *skip != 0) return;
-    __shared__ double s_rsum[MODE == MODE_RELAX ? EPB * B : 1];
+    __shared__ __align__(16) double s_rsum[MODE == MODE_RELAX ? EPB * B : 2];
     __shared__ double s_red[32];
-    const int el = threadIdx.x / B;
-    const int r = threadIdx.x - el * B;
+    const int rowid = threadIdx.x / LP, h = threadIdx.x - rowid * LP;
+    const int el = rowid / B;
+    const int r = rowid - el * B;
     const bool lane_ok = el < EPB;
+    const bool writer = h == 0;               // the lane that owns the row's result
     const int ntiles = (sel.count + EPB - 1) / EPB;
     double sumsq = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -88,22 +113,25 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
             for (int jj = j0; jj < j1; ++jj) {
                 const int col = indices[jj];
                 if (MODE == MODE_RELAX && col == e) continue;
-                acc += row_dot<B>(data + ((size_t)jj * B + r) * B, x_in + (size_t)col * B);
+                acc += row_dot_part<B, LP>(data + ((size_t)jj * B + r) * B, x_in + (size_t)col * B, h);
             }
         }
+        if (LP == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);      // the two halves of the row
         if (MODE == MODE_APPLY) {
-            if (e >= 0) x_out[(size_t)e * B + r] = acc;
+            if (e >= 0 && writer) x_out[(size_t)e * B + r] = acc;
         } else if (MODE == MODE_RESIDUAL) {
-            if (e >= 0) {
+            if (e >= 0 && writer) {
                 const double res = rhs[(size_t)e * B + r] - acc;
                 if (x_out != nullptr) x_out[(size_t)e * B + r] = res;
                 sumsq = fma(res, res, sumsq);
             }
         } else {
-            if (e >= 0) s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
+            if (e >= 0 && writer) s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
             __syncthreads();
-            if (e >= 0) {
-                const double t = row_dot<B>(dinv + ((size_t)e * B + r) * B, s_rsum + el * B);
+            double t = 0.0;
+            if (e >= 0) t = row_dot_part<B, LP>(dinv + ((size_t)e * B + r) * B, s_rsum + el * B, h);
+            if (LP == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if (e >= 0 && writer) {
                 const double xo = x_in[(size_t)e * B + r];
                 x_out[(size_t)e * B + r] = (omega == 1.0) ? t : omega * t + (1.0 - omega) * xo;
             }
