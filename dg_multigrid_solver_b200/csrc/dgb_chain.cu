@@ -21,7 +21,9 @@
 //                over through a shared-memory ring (same CTA) or the level's global mailbox (next CTA).
 //
 // The sweep order, and therefore the result up to rounding of the re-associated products, is exactly the
-// reference's.  Periodic grids (O-grid wrap) keep the row-pipelined kernel of dgb_stream.cu.
+// reference's.  O-grids (periodic in i): the LAST element of a row has a third earlier neighbour, the row's first
+// element across the wrap; its pre-multiplied block lives in a small side array (one per row and direction) and
+// is applied by the fill/drain path of the chain kernel.  Grids periodic in j keep the row-pipelined kernel.
 #include "dgb_async.cuh"
 #include "dgb_common.cuh"
 
@@ -138,9 +140,10 @@ struct ChainRow {
     }
     // x = c - M_row x_prev - M_up x_up   (records hold the negated products); with P > 1 the partial sums of the
     // P lanes of a scalar row are added by shuffles and the result is valid in the lane with part == 0
-    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN]) const {
+    // extra: this lane's share of one more (negated) product, added before the lanes of a row are summed
+    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN], double extra = 0.0) const {
         if (P == 1) {
-            double a0 = c, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double a0 = c + extra, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
             for (int k = 0; k < CW; ++k) {
                 if (k & 1) {
@@ -159,7 +162,7 @@ struct ChainRow {
             s1 = fma(ml[k], p[k], s1);
             s2 = fma(mu[k], u[k], s2);
         }
-        const double mine = s1 + s2;
+        const double mine = (s1 + s2) + extra;
         double sum = mine;
 #pragma unroll
         for (int o = 1; o < P; ++o) sum += __shfl_down_sync(0xffffffffu, mine, o);
@@ -246,8 +249,8 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
 
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
-k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, double *__restrict__ x, double *mbox,
-           Stencil S_, int *work, int *err, const int32_t *__restrict__ skip) {
+k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const double *__restrict__ wrapm,
+           double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err, const int32_t *__restrict__ skip) {
     using C = ChainCfg<B>;
     constexpr int B2 = C::B2, R = C::R, REC = C::REC, CH = C::CH, NS = C::NS, RING = C::RING, BP = C::BP;
     constexpr int RINGR = C::RINGR, WR = C::WR, RRS = C::RRS, PCH = C::PCH, PSL = C::PSL;
@@ -388,6 +391,17 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
     asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
+    // O-grid: my entries of the block that couples the row's last element to its first one (wrapm[row][B2],
+    // lane-major like the record blocks), and the first element's new value (picked up one step after it is made)
+    constexpr bool PER_OK = B != 25;            // (b=25 has no registers to spare: its O-grid levels keep k_gs_rows)
+    constexpr int WN = PER_OK ? CW : 1;
+    const int per = PER_OK ? S_.per_i : 0;
+    double mw[WN], xf[WN];
+#pragma unroll
+    for (int k = 0; k < WN; ++k) {
+        mw[k] = per ? wrapm[(size_t)j * B2 + C::mat_offset(r, part * CW + k)] : 0.0;
+        xf[k] = 0.0;
+    }
     // my entry of c in the OTHER direction's record of sweep index idx: a constant stride of -R records per step
     // (the opposite sweep visits the rows and the columns in reverse order)
     double *corow;
@@ -434,8 +448,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
         const uint32_t si0 = (uint32_t)(t0 % RING) * S;                       // incoming-ring slot of column t0
         const uint32_t sr0b = (uint32_t)(t0 % RINGR) * S;                     // row-ring slot of step t0 (0 if RINGR == CH)
         uint32_t sm = rec_m + (uint32_t)s * (CH * KS), sc = rec_c + (uint32_t)s * (CH * KS);
-        if (t0 >= R - 1 && t0 + CH <= Ni) {
-            // ---- every row of the band is inside the grid for all CH steps: no predicates, immediates ----
+        if (t0 >= R - 1 + 2 * per && t0 + CH <= Ni - per) {
+            // ---- every row of the band is inside the grid for all CH steps (O-grid: and none of them is at the
+            // row's second or last element): no predicates, immediates ----
             // vector of the row above: row 0 reads column t0 + k of the incoming ring, row g > 0 the slot of step t0 + k - 1
             uint32_t ua0, ua, pa0, pa, ow;
             if (RINGR == CH) {
@@ -507,7 +522,18 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, doubl
                 }
                 ChainRow<B> row;
                 row.load(sm + k * KS, sc + k * KS);
-                const double xnew = row.eval(p, u);
+                double extra = 0.0;
+                if (PER_OK && per) {
+                    if (idx == 1) {                     // p holds the new value of the row's first element
+#pragma unroll
+                        for (int q = 0; q < WN; ++q) xf[q] = p[q];
+                    }
+                    if (idx == Ni - 1) {                // the wrap neighbour is an earlier element of the sweep
+#pragma unroll
+                        for (int q = 0; q < WN; ++q) extra = fma(mw[q], xf[q], extra);
+                    }
+                }
+                const double xnew = row.eval(p, u, extra);
                 if (poll && fin) sts1(uk + 8 * r, sentinel);
                 if (act) {
                     sts1(own_b + so + 8 * r, xnew);
@@ -568,12 +594,15 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             const int j = e / Ni, i = e - j * Ni;
             const int e_row = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;       // handled by the chain
             const int e_up = S_.active(j - dir) ? e - dir * Ni : -1;               // handled by the chain
+            // O-grid: the last element of the row meets the (already updated) first one across the wrap
+            const int e_wrap = (S_.per_i && i == (dir > 0 ? Ni - 1 : 0)) ? e - dir * (Ni - 1) : -1;
             double acc = 0.0, acc_chain = 0.0;
             for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
                 const int col = indices[jj];
                 // RES (entry of a smoother call): neighbours in ghost rows are left to the edge kernel of the pass
                 // that follows (dgb_block_gs_pass_seq), which sees the halo values of that moment
-                const bool chain_part = col == e || col == e_row || col == e_up || (RES && (col < first || col >= first + count));
+                const bool chain_part = col == e || col == e_row || col == e_up || col == e_wrap ||
+                                        (RES && (col < first || col >= first + count));
                 if (!RES && chain_part) continue;
                 const double tt = row_dot<B>(data + ((size_t)jj * B + r) * B, x + (size_t)col * B);
                 if (chain_part) acc_chain += tt;
@@ -694,6 +723,30 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
         if (S_.active(j))
             rec[((size_t)(slot >> 1) * chain_dir_records<B>(S_) + (size_t)chain_loc<B>(S_, dir, i, j)) * REC + (slot & 1) * B2 + ChainCfg<B>::mat_offset(r, c)] = v;
     }
+    if (!S_.per_i) return;
+    // O-grid: wrap[dir][row j] = -Dinv_e A_e,first for the row's last element e in that sweep direction
+    double *wrap = rec + 2 * (size_t)chain_dir_records<B>(S_) * REC;
+    const long long wtotal = 2LL * S_.Nj * B2;
+    for (long long tt = (long long)blockIdx.x * 256 + threadIdx.x; tt < wtotal; tt += (long long)gridDim.x * 256) {
+        const int d01 = (int)(tt / ((long long)S_.Nj * B2));
+        const int rem = (int)(tt - (long long)d01 * S_.Nj * B2);
+        const int j = rem / B2, rc = rem - j * B2;
+        const int r = rc / B, c = rc - r * B;
+        const int dir = d01 == 0 ? 1 : -1;
+        const int e = j * Ni + (dir > 0 ? Ni - 1 : 0), col = j * Ni + (dir > 0 ? 0 : Ni - 1);
+        double v = 0.0;
+        if (S_.active(j)) {
+            for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+                if (indices[jj] != col) continue;
+                const double *d = dinv + ((size_t)e * B + r) * B;
+                const double *a = data + (size_t)jj * B2 + c;
+                double sacc = 0.0;
+                for (int k = 0; k < B; ++k) sacc = fma(d[k], a[k * B], sacc);
+                v -= sacc;
+            }
+        }
+        wrap[((size_t)d01 * S_.Nj + j) * B2 + ChainCfg<B>::mat_offset(r, c)] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -704,8 +757,12 @@ int g_chain_mask = 15;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : 0;
-    return flags >= 0 && (flags & 3) == 0 && (g_chain_mask & bit) != 0;
+    // periodic in j (fully periodic grids) is not handled; b=25 has no registers left for the wrap block
+    return flags >= 0 && (flags & DGB_FLAG_PERIODIC_J) == 0 && !((flags & DGB_FLAG_PERIODIC_I) && b == 25) &&
+           (g_chain_mask & bit) != 0;
 }
+// O-grids need three distinct elements per row (else the wrap neighbour coincides with the row neighbour)
+static bool chain_shape_ok(int Ni, int flags) { return !(flags & DGB_FLAG_PERIODIC_I) || Ni >= 3; }
 // doubles of one direction's record stream
 static long long chain_dir_len(int b, const Stencil &S_) {
     switch (b) {
@@ -720,8 +777,8 @@ static long long chain_dir_len(int b, const Stencil &S_) {
 int g_chain_cluster = 8;        // CTAs per cluster of the chain kernel (tuning: dgb_set_kernel_path(400 + n))
 
 template <int B, int W, int DIR>
-static int chain_launch_d(const double *rec, double *rec_other, double *x, double *mbox, Stencil S_,
-                          const int32_t *skip, cudaStream_t st) {
+static int chain_launch_d(const double *rec, double *rec_other, const double *wrapm, double *x, double *mbox,
+                          Stencil S_, const int32_t *skip, cudaStream_t st) {
     using C = ChainCfg<B>;
     static bool configured = false;
     static int max_cluster = 1;
@@ -767,16 +824,16 @@ static int chain_launch_d(const double *rec, double *rec_other, double *x, doubl
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    DGB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rec, rec_other, x, mbox, S_, work_ptr(), err_ptr(), skip));
+    DGB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rec, rec_other, wrapm, x, mbox, S_, work_ptr(), err_ptr(), skip));
     DGB_LAUNCH_OK();
     return 0;
 }
 
 template <int B, int W>
-static int chain_launch_w(const double *rec, double *rec_other, double *x, double *mbox, Stencil S_, int dir,
-                          const int32_t *skip, cudaStream_t st) {
-    return dir > 0 ? chain_launch_d<B, W, 1>(rec, rec_other, x, mbox, S_, skip, st)
-                   : chain_launch_d<B, W, -1>(rec, rec_other, x, mbox, S_, skip, st);
+static int chain_launch_w(const double *rec, double *rec_other, const double *wrapm, double *x, double *mbox,
+                          Stencil S_, int dir, const int32_t *skip, cudaStream_t st) {
+    return dir > 0 ? chain_launch_d<B, W, 1>(rec, rec_other, wrapm, x, mbox, S_, skip, st)
+                   : chain_launch_d<B, W, -1>(rec, rec_other, wrapm, x, mbox, S_, skip, st);
 }
 
 bool chain_c_recurrence(int flags);
@@ -807,8 +864,10 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
         DGB_LAUNCH_OK();
     }
     if (g_gs_variant == 21) return 0;
-    if (B <= 9 && g_gs_variant == 11) return chain_launch_w<B, 2>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
-    return chain_launch_w<B, C::WDEF>(rec, rec_other, x, op->gs_mailbox, S_, dir, skip, st);
+    // O-grid: wrap blocks behind the two record streams, [direction][row][B2]
+    const double *wrapm = op->gs_chain + 2 * chain_dir_len(B, S_) + (dir > 0 ? 0 : (long long)S_.Nj * C::B2);
+    if (B <= 9 && g_gs_variant == 11) return chain_launch_w<B, 2>(rec, rec_other, wrapm, x, op->gs_mailbox, S_, dir, skip, st);
+    return chain_launch_w<B, C::WDEF>(rec, rec_other, wrapm, x, op->gs_mailbox, S_, dir, skip, st);
 }
 
 // helper of the pass in direction `dir` fused with the residual r = rhs - A x (r may be NULL) and its per-CTA
@@ -866,13 +925,14 @@ using namespace dgb;
 extern "C" {
 
 int64_t dgb_gs_chain_len(int32_t b, int32_t Ni, int32_t Nj, int32_t stencil) {
-    if (!chain_supported(b, stencil) || Ni <= 0 || Nj <= 0) return 0;
-    return 2 * (int64_t)chain_dir_len(b, make_stencil(Ni, Nj, stencil)) + 2;
+    if (!chain_supported(b, stencil) || Ni <= 0 || Nj <= 0 || !chain_shape_ok(Ni, stencil)) return 0;
+    return 2 * (int64_t)chain_dir_len(b, make_stencil(Ni, Nj, stencil)) +
+           ((stencil & DGB_FLAG_PERIODIC_I) ? 2 * (int64_t)Nj * b * b : 0) + 2;
 }
 
 int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
     DGB_ARG(op != nullptr && op->data && op->indices && op->indptr && op->dinv && op->gs_chain);
-    DGB_ARG(chain_supported(op->b, op->stencil));
+    DGB_ARG(chain_supported(op->b, op->stencil) && chain_shape_ok(op->Ni, op->stencil));
     cudaStream_t st = (cudaStream_t)stream;
     const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
     const long long N = (long long)op->Ni * op->Nj;

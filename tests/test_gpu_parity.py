@@ -433,3 +433,26 @@ def test_vcycle_result_copied_out_on_second_stream():
         got = d.solver.multigrid_V_cycle(k=k, RHS=rhs_h, u=u_h, out=out)
         assert got is out
         assert np.array_equal(out.numpy(), u_plain)
+
+
+@pytest.mark.parametrize("Ni,Nj,P", [(3, 4, 1), (8, 5, 1), (17, 9, 2), (12, 6, 3), (40, 30, 1), (64, 20, 2)])
+def test_chained_gauss_seidel_kernel_ogrid(Ni, Nj, P):
+    """The same checks on O-grids (periodic in i): the last element of every row also meets the row's first
+    element across the wrap (side array of wrap blocks, fill/drain path of the chain kernel)."""
+    from dg_multigrid_solver_b200 import _lib
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    x, y = _synthetic("circ", Ni, Nj, P)
+    case = dict(grid="synthetic.xyz", pg=P, pu=P, ogrid=True, circ=True, sigmul=2.0)
+    s = make_settings(case)
+    geo = Geometry(None, s, nodes=(np.ascontiguousarray(x.T), np.ascontiguousarray(y.T)))
+    L = _lib.load()
+    L.dgb_set_kernel_path(300 + 15)
+    try:
+        d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg",
+                  write_results=False)
+        grid = d.grids[-1]
+        assert grid.d_chain is not None, "chained kernel not selected"
+        _chained_gs_checks(grid, Ni, Nj, L)
+    finally:
+        L.dgb_set_kernel_path(300 + CHAIN_MASK_DEFAULT)

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python tools/bench_configs.py c5 1024 > gpurun_out/c5.json 2>/dev/null; cut -c1-700 gpurun_out/c5.json
-timeout 900 python tools/bench_configs.py c4 1024 > gpurun_out/c4.json 2>/dev/null; cut -c1-1100 gpurun_out/c4.json
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; tail -12 gpurun_out/pytest_gpu.log | cut -c1-400
