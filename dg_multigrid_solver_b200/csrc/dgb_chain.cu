@@ -41,7 +41,7 @@ struct ChainCfg {
     static constexpr int P = B == 9 ? 3 : B == 16 ? 2 : 1;            // lanes per scalar row (each takes B/P columns)
     static constexpr int CW = B / P;                                  // matrix columns per lane
     static constexpr int LPR = B * P;                                 // lanes per element row
-    static constexpr int R = 32 / LPR;                                // element rows per warp
+    static constexpr int R = LPR > 32 ? 1 : 32 / LPR;                 // element rows per warp (b=36: k_gs_chain_big)
     static constexpr int VN = P == 1 ? ((B + 1) & ~1) : CW;           // vector entries a lane loads
     // the two blocks of a record are stored lane-major, MV doubles at a time, so that the lanes of an element row
     // read consecutive shared-memory words (no bank conflicts): entry (r, c) of a block sits at mat_offset(r, c)
@@ -51,7 +51,7 @@ struct ChainCfg {
     }
     static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
     static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 4 : 1;           // steps per chunk (one bulk copy)
-    static constexpr int NS = (B == 9 || B == 16) ? 2 : 3;            // bulk-copy stages
+    static constexpr int NS = (B == 9 || B == 16 || B == 36) ? 2 : 3; // bulk-copy stages
     static constexpr int RING = B <= 9 ? 32 : 16;                     // columns per band hand-over ring
     static constexpr int RINGR = CH < 2 ? 2 : CH;                     // steps per row ring (rows of one warp)
     static constexpr int BP = (B + 1) & ~1;                           // doubles per ring slot
@@ -562,6 +562,239 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     }
 }
 
+
+// =========================================================================================
+// k_gs_chain_big: the same chain for blocks with more scalar rows than a warp has lanes (b = 36, p = 5).
+// One element row per warp, lane q < b/2 owns the scalar rows 2q and 2q+1; the two b x b products are streamed
+// through the lanes 16 bytes at a time (nothing but eight accumulators stays in registers); one record, i.e. one
+// step, per bulk copy.  Rings, mailbox, clusters, tickets and the record stream are those of k_gs_chain.
+// =========================================================================================
+__device__ __forceinline__ void sts2(uint32_t a, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts2_cluster(uint32_t a, double2 v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+
+template <int B>
+struct BigCfg {
+    using C = ChainCfg<B>;
+    static constexpr int LPL = B / 2;                                  // working lanes
+    __host__ __device__ static constexpr size_t o_xf(int W) { return C::smem(W); }
+    __host__ __device__ static constexpr size_t smem(int W) { return ((o_xf(W) + 15) & ~(size_t)15) + sizeof(double) * W * B; }
+};
+
+// rows 2q, 2q+1 of  c + M_row p + M_up u  for one staged record; *bad: some entry of u is the "not delivered" mark
+template <int B>
+__device__ __forceinline__ double2 big_eval(uint32_t rec_a /* record */, uint32_t pa, uint32_t ua, int q, bool *bad) {
+    constexpr int B2 = B * B;
+    const uint32_t m = rec_a + (uint32_t)(q * 32);                     // my two rows of a 16-byte column pair
+    const double2 cc = lds2(rec_a + (uint32_t)((2 * B2 + 2 * q) * 8));
+    double a0 = cc.x, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = cc.y, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    unsigned mx = 0u;
+#pragma unroll
+    for (int k = 0; k < B / 2; ++k) {
+        const double2 pp = lds2(pa + k * 16), uu = lds2(ua + k * 16);
+        mx = max(mx, max((unsigned)__double2hiint(uu.x), (unsigned)__double2hiint(uu.y)));
+        const double2 ra = lds2(m + k * (2 * B * 8)), rb = lds2(m + k * (2 * B * 8) + 16);
+        const double2 sa = lds2(m + (B2 + k * 2 * B) * 8), sb = lds2(m + (B2 + k * 2 * B) * 8 + 16);
+        a0 = fma(ra.x, pp.x, a0); a1 = fma(ra.y, pp.y, a1);
+        b0 = fma(rb.x, pp.x, b0); b1 = fma(rb.y, pp.y, b1);
+        a2 = fma(sa.x, uu.x, a2); a3 = fma(sa.y, uu.y, a3);
+        b2 = fma(sb.x, uu.x, b2); b3 = fma(sb.y, uu.y, b3);
+    }
+    *bad = mx == 0xffffffffu;
+    return make_double2((a0 + a1) + (a2 + a3), (b0 + b1) + (b2 + b3));
+}
+
+template <int B, int W, int DIR>
+__global__ void __launch_bounds__(W * 32)
+k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, const double *__restrict__ wrapm,
+               double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err,
+               const int32_t *__restrict__ skip) {
+    using C = ChainCfg<B>;
+    constexpr int B2 = C::B2, REC = C::REC, NS = C::NS, RING = C::RING, BP = C::BP, WR = C::WR;
+    constexpr int PCH = C::PCH, PSL = C::PSL, LPL = BigCfg<B>::LPL;
+    constexpr uint32_t S = BP * 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(C::R == 1 && C::CH == 1 && C::RINGR == 2 && B % 2 == 0, "one row and one step per chunk");
+    if (skip != nullptr && *skip != 0) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_ticket;
+    double *stages = reinterpret_cast<double *>(smem);
+    double *rings = reinterpret_cast<double *>(smem + C::o_ring(W));
+    double *scratch = reinterpret_cast<double *>(smem + C::o_scr(W));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::o_bar(W));
+    volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::o_prog(W));
+    double *xfirst = reinterpret_cast<double *>(smem + ((BigCfg<B>::o_xf(W) + 15) & ~(size_t)15));
+    const double sentinel = __longlong_as_double(-1LL);
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    if (crank == 0 && threadIdx.x == 0) {
+        const int tk = atomicAdd(&work[0], 1);
+        for (uint32_t c = 0; c < csize; ++c) sts_cluster_u32(cluster_map(smem_u32(&s_ticket), c), tk);
+    }
+    if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
+    for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
+    if ((threadIdx.x & 31) == 0) {
+        uint64_t *bw = bars + (threadIdx.x >> 5) * NS;
+        for (int s = 0; s < NS; ++s) mbar_init(&bw[s], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    cluster_sync_all();
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(w));
+    asm volatile("" : "+r"(lane));
+    const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
+    const int sr = (s_ticket * (int)csize + (int)crank) * W + w;       // my row, in sweep order
+    if (sr >= nrows) return;
+    uint64_t *full = bars + w * NS;
+    const int q = lane % LPL;                        // lanes >= LPL shadow the first ones (they never store)
+    const bool live = lane < LPL;
+    const int j = DIR > 0 ? S_.ja0 + sr : S_.ja1 - 1 - sr;
+    int pred = sr == 0 ? 0 : ((w > 0 || crank > 0) ? 1 : 2);
+    int succ = sr + 1 >= nrows ? 0 : (w < W - 1 ? 1 : (crank + 1 < csize ? 3 : 2));
+    asm volatile("" : "+r"(pred), "+r"(succ));
+    double *wstage = stages + (size_t)w * (NS * REC);
+    double *inring = rings + (size_t)w * WR;
+    double *rowring = inring + RING * BP;                              // two slots: previous / current column
+    double *outr = rings + (size_t)(w + 1) * WR;
+    double *xf = xfirst + (size_t)w * B;
+    const double *bsrc = rec + (size_t)sr * Ni * REC;                  // R = 1: band = row, T = Ni
+    auto issue = [&](int n) {
+        const int s = n % NS;
+        mbar_expect_tx(&full[s], (uint32_t)(REC * 8));
+        bulk_g2s(wstage + (size_t)s * REC, bsrc + (size_t)n * REC, (uint32_t)(REC * 8), &full[s]);
+    };
+    if (lane == 0)
+        for (int n = 0; n < NS && n < Ni; ++n) issue(n);
+
+    const size_t mrow = (size_t)(j - DIR) * Ni;
+    double PV[PSL];
+    auto mb_load = [&](int m) {
+#pragma unroll
+        for (int sl = 0; sl < PSL; ++sl) {
+            const int e = lane + 32 * sl;
+            const int col = m * PCH + e / B;
+            PV[sl] = 0.0;
+            if (e < PCH * B && col < Ni) PV[sl] = __ldcg(mbox + (mrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (e % B));
+        }
+    };
+    auto mb_take = [&](int m) -> bool {
+        for (int spin = 0;; ++spin) {
+            bool mine = true;
+#pragma unroll
+            for (int sl = 0; sl < PSL; ++sl) {
+                const int e = lane + 32 * sl;
+                if (e < PCH * B && m * PCH + e / B < Ni && chain_sentinel(PV[sl])) mine = false;
+            }
+            if (__all_sync(FULL, mine)) break;
+            if (spin > kSpinLimit || ((spin & 63) == 63 && *(volatile int *)err != 0)) {
+                if (lane == 0) atomicExch(err, 2);
+                return false;
+            }
+            mb_load(m);
+        }
+#pragma unroll
+        for (int sl = 0; sl < PSL; ++sl) {
+            const int e = lane + 32 * sl;
+            const int col = m * PCH + e / B;
+            if (e < PCH * B && col < Ni) {
+                inring[(col % RING) * BP + (e % B)] = PV[sl];
+                __stcg(mbox + (mrow + (DIR > 0 ? col : Ni - 1 - col)) * B + (e % B), sentinel);
+            }
+        }
+        if ((m + 1) * PCH < Ni) mb_load(m + 1);
+        return true;
+    };
+    if (pred == 2) mb_load(0);
+
+    const uint32_t in_b = smem_u32(inring), row_b = smem_u32(rowring), scr = smem_u32(scratch);
+    const uint32_t out_b = (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank));
+    const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
+                                         : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
+    const uint32_t stage0 = smem_u32(wstage);
+    double *xrow = x + (size_t)j * Ni * B + 2 * q;
+    const int sro = nrows - 1 - sr;                                    // my row in the opposite sweep order
+    double *corow = rec_other + ((size_t)sro * Ni + (Ni - 1)) * REC + 2 * B2 + 2 * q;      // idx = 0, stride -REC
+    const double *wrow = wrapm + (size_t)j * B2;                       // O-grid: wrap block of my row
+    const int per = S_.per_i;
+    int prog_seen = 0;
+    for (int t = 0; t < Ni; ++t) {
+        const int s = t % NS;
+        if (!mbar_wait(&full[s], (uint32_t)((t / NS) & 1), err)) return;
+        if (pred == 1 && lane == 0) s_prog[w] = t;
+        if (succ == 1 || succ == 3) {
+            if (prog_seen < t + 1 - RING) {
+                int spin = 0;
+                while ((prog_seen = ldv_cluster_s32(prog_next)) < t + 1 - RING) {
+                    if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+                        if (lane == 0) atomicExch(err, 2);
+                        return;
+                    }
+                }
+            }
+            if ((t & 3) == 0) prog_seen = ldv_cluster_s32(prog_next);
+        }
+        if (pred != 1 && (t % PCH) == 0) {
+            if (pred == 2) {
+                if (!mb_take(t / PCH)) return;
+            } else {
+                for (int e = lane; e < PCH * BP; e += 32) inring[((t + e / BP) % RING) * BP + (e % BP)] = 0.0;
+            }
+            __syncwarp();
+        }
+        const uint32_t ua = in_b + (uint32_t)(t % RING) * S;           // the row above, this column
+        const uint32_t pa = row_b + (uint32_t)((t + 1) & 1) * S;       // my row, previous column
+        const uint32_t ra = stage0 + (uint32_t)s * (REC * 8);
+        bool bad;
+        double2 xn = big_eval<B>(ra, pa, ua, q, &bad);
+        if (__any_sync(FULL, bad)) {
+            if (!chain_wait_up<B>(ua, err)) return;
+            xn = big_eval<B>(ra, pa, ua, q, &bad);
+        }
+        if (per) {
+            if (t == 1 && live) {                                      // the first element's new value
+                const double2 f = lds2(pa + q * 16);
+                xf[2 * q] = f.x;
+                xf[2 * q + 1] = f.y;
+            }
+            if (t == Ni - 1) {                                         // wrap neighbour: an earlier element
+                __syncwarp();
+                double ea = 0.0, eb = 0.0;
+                for (int k = 0; k < B / 2; ++k) {
+                    const double2 f = *reinterpret_cast<const double2 *>(xf + 2 * k);
+                    const double2 wa = *reinterpret_cast<const double2 *>(wrow + C::mat_offset(2 * q, 2 * k));
+                    const double2 wb = *reinterpret_cast<const double2 *>(wrow + C::mat_offset(2 * q + 1, 2 * k));
+                    ea = fma(wa.x, f.x, ea); ea = fma(wa.y, f.y, ea);
+                    eb = fma(wb.x, f.x, eb); eb = fma(wb.y, f.y, eb);
+                }
+                xn.x += ea;
+                xn.y += eb;
+            }
+        }
+        if (live) {
+            const double2 cd = lds2(ra + (uint32_t)((2 * B2 + 2 * q) * 8)), dd = lds2(ra + (uint32_t)((2 * B2 + B + 2 * q) * 8));
+            sts2(ua + q * 16, make_double2(sentinel, sentinel));                  // hand the incoming slot back
+            sts2(row_b + (uint32_t)(t & 1) * S + q * 16, xn);
+            sts2_cluster(out_b + (uint32_t)(t % RING) * S + q * 16, xn);
+            const int i = DIR > 0 ? t : Ni - 1 - t;
+            *reinterpret_cast<double2 *>(xrow + (size_t)i * B) = xn;
+            *reinterpret_cast<double2 *>(corow - (size_t)t * REC) = make_double2((dd.x - cd.x) + xn.x, (dd.y - cd.y) + xn.y);
+            if (succ == 2) {
+                __stcg(mbox + ((size_t)j * Ni + i) * B + 2 * q, xn.x);
+                __stcg(mbox + ((size_t)j * Ni + i) * B + 2 * q + 1, xn.y);
+            }
+        }
+        (void)scr;
+        __syncwarp();
+        if (lane == 0 && t + NS < Ni) {
+            fence_proxy_async();
+            issue(t + NS);
+        }
+    }
+}
+
 // ---- the parallel part: c_e = Dinv_e (rhs_e - sum over the neighbours the chain does not handle) ----
 template <int B>
 struct HelperCfg {
@@ -751,12 +984,12 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
 
 // ---------------------------------------------------------------------------------------
 // host side
-// block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25
+// block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25, bit 4 b=36
 // (dgb_set_kernel_path(300 + mask); the default follows the measurements in profiles/)
 int g_chain_mask = 15;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
-    const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : 0;
+    const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : b == 36 ? 16 : 0;
     // periodic in j (fully periodic grids) is not handled; b=25 has no registers left for the wrap block
     return flags >= 0 && (flags & DGB_FLAG_PERIODIC_J) == 0 && !((flags & DGB_FLAG_PERIODIC_I) && b == 25) &&
            (g_chain_mask & bit) != 0;
@@ -770,6 +1003,7 @@ static long long chain_dir_len(int b, const Stencil &S_) {
     case 9: return chain_dir_records<9>(S_) * ChainCfg<9>::REC;
     case 16: return chain_dir_records<16>(S_) * ChainCfg<16>::REC;
     case 25: return chain_dir_records<25>(S_) * ChainCfg<25>::REC;
+    case 36: return chain_dir_records<36>(S_) * ChainCfg<36>::REC;
     }
     return 0;
 }
@@ -896,9 +1130,90 @@ int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const do
     case 9: return helper_residual_t<9>(op, rhs, x, dir, r, partials, grid_out, st);
     case 16: return helper_residual_t<16>(op, rhs, x, dir, r, partials, grid_out, st);
     case 25: return helper_residual_t<25>(op, rhs, x, dir, r, partials, grid_out, st);
+    case 36: return helper_residual_t<36>(op, rhs, x, dir, r, partials, grid_out, st);
     }
     set_error("gs_chain_helper_residual: unsupported block size b=%d", op->b);
     return 2;
+}
+
+template <int B, int W, int DIR>
+static int big_launch_d(const double *rec, double *rec_other, const double *wrapm, double *x, double *mbox,
+                        Stencil S_, const int32_t *skip, cudaStream_t st) {
+    static bool configured = false;
+    static int max_cluster = 1;
+    auto kern = k_gs_chain_big<B, W, DIR>;
+    const size_t smem = BigCfg<B>::smem(W);
+    if (!configured) {
+        DGB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int cs = 8; cs >= 1; cs >>= 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs, 1, 1);
+            cfg.blockDim = dim3(W * 32, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
+                max_cluster = cs;
+                break;
+            }
+            (void)cudaGetLastError();
+        }
+        configured = true;
+    }
+    DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
+    const int nctas = (S_.ja1 - S_.ja0 + W - 1) / W;
+    int cs = 1;
+    while (cs * 2 <= max_cluster && cs * 2 <= g_chain_cluster && cs < nctas) cs *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((nctas + cs - 1) / cs) * cs), 1, 1);
+    cfg.blockDim = dim3(W * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    DGB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rec, rec_other, wrapm, x, mbox, S_, work_ptr(), err_ptr(), skip));
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+template <int B>
+static int chain_pass_big(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c,
+                          const int32_t *skip, cudaStream_t st) {
+    using C = ChainCfg<B>;
+    using H = HelperCfg<B>;
+    const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
+    double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
+    double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
+    const int count = (S_.ja1 - S_.ja0) * S_.Ni;
+    int grid = (count + H::EPB - 1) / H::EPB;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    if (have_c && !chain_c_recurrence(op->stencil)) {
+        const int edge = ((S_.ja0 > 0) + (S_.ja1 < S_.Nj)) * S_.Ni;
+        int ge = (edge + H::EPB - 1) / H::EPB;
+        if (ge > sm_count() * 8) ge = sm_count() * 8;
+        k_gs_edge_helper<B><<<ge, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, x, rec, S_, dir, skip);
+        DGB_LAUNCH_OK();
+    }
+    if (!have_c && g_gs_variant != 22) {
+        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
+                                                      S_, dir, skip, nullptr, nullptr);
+        DGB_LAUNCH_OK();
+    }
+    if (g_gs_variant == 21) return 0;
+    const double *wrapm = op->gs_chain + 2 * chain_dir_len(B, S_) + (dir > 0 ? 0 : (long long)S_.Nj * C::B2);
+    return dir > 0 ? big_launch_d<B, C::WDEF, 1>(rec, rec_other, wrapm, x, op->gs_mailbox, S_, skip, st)
+                   : big_launch_d<B, C::WDEF, -1>(rec, rec_other, wrapm, x, op->gs_mailbox, S_, skip, st);
 }
 
 // the opposite-direction c left behind by a chain pass is complete only when no neighbour lives in a ghost row
@@ -913,6 +1228,7 @@ int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir,
     case 9: return chain_pass_t<9>(op, rhs, x, dir, have_c, skip, st);
     case 16: return chain_pass_t<16>(op, rhs, x, dir, have_c, skip, st);
     case 25: return chain_pass_t<25>(op, rhs, x, dir, have_c, skip, st);
+    case 36: return chain_pass_big<36>(op, rhs, x, dir, have_c, skip, st);
     }
     set_error("gs_chain_pass: unsupported block size b=%d", op->b);
     return 2;
@@ -944,6 +1260,7 @@ int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
     case 9: k_build_gs_chain<9><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
     case 16: k_build_gs_chain<16><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
     case 25: k_build_gs_chain<25><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    case 36: k_build_gs_chain<36><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
     }
     DGB_LAUNCH_OK();
     return 0;
