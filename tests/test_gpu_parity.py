@@ -353,7 +353,7 @@ def test_stokes_local_order_assembly(name):
 
 @pytest.mark.parametrize("Ni,Nj,P", [
     (3, 5, 1), (1, 7, 1), (7, 1, 2), (2, 2, 1), (17, 9, 2), (40, 33, 1), (33, 40, 2), (8, 8, 3), (6, 7, 4),
-    (64, 64, 1), (130, 70, 2), (70, 130, 1),
+    (64, 64, 1), (130, 70, 2), (70, 130, 1), (5, 4, 5), (1, 3, 5), (24, 37, 5),
 ])
 def test_chained_gauss_seidel_kernel(Ni, Nj, P):
     """k_gs_helper + k_gs_chain (dgb_chain.cu) on ragged grid shapes -- partial bands, single rows/columns,
@@ -370,7 +370,7 @@ def test_chained_gauss_seidel_kernel(Ni, Nj, P):
     s = make_settings(case)
     geo = Geometry(None, s, nodes=(np.ascontiguousarray(x.T), np.ascontiguousarray(y.T)))
     L = _lib.load()
-    L.dgb_set_kernel_path(300 + 15)         # chained kernel for every block size it supports
+    L.dgb_set_kernel_path(300 + 31)         # chained kernel for every block size it supports
     try:
         d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg",
                   write_results=False)
@@ -435,7 +435,8 @@ def test_vcycle_result_copied_out_on_second_stream():
         assert np.array_equal(out.numpy(), u_plain)
 
 
-@pytest.mark.parametrize("Ni,Nj,P", [(3, 4, 1), (8, 5, 1), (17, 9, 2), (12, 6, 3), (40, 30, 1), (64, 20, 2)])
+@pytest.mark.parametrize("Ni,Nj,P", [(3, 4, 1), (8, 5, 1), (17, 9, 2), (12, 6, 3), (40, 30, 1), (64, 20, 2), (3, 2, 5),
+                                     (20, 35, 5)])
 def test_chained_gauss_seidel_kernel_ogrid(Ni, Nj, P):
     """The same checks on O-grids (periodic in i): the last element of every row also meets the row's first
     element across the wrap (side array of wrap blocks, fill/drain path of the chain kernel)."""
@@ -447,7 +448,7 @@ def test_chained_gauss_seidel_kernel_ogrid(Ni, Nj, P):
     s = make_settings(case)
     geo = Geometry(None, s, nodes=(np.ascontiguousarray(x.T), np.ascontiguousarray(y.T)))
     L = _lib.load()
-    L.dgb_set_kernel_path(300 + 15)
+    L.dgb_set_kernel_path(300 + 31)
     try:
         d = DGFEM(settings=s, geometry=geo, solve_smoother=True, smoother="block_gauss_seidel_pyamg",
                   write_results=False)
