@@ -986,7 +986,7 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
 // host side
 // block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25, bit 4 b=36
 // (dgb_set_kernel_path(300 + mask); the default follows the measurements in profiles/)
-int g_chain_mask = 15;
+int g_chain_mask = 31;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : b == 36 ? 16 : 0;

@@ -381,7 +381,7 @@ def test_chained_gauss_seidel_kernel(Ni, Nj, P):
         L.dgb_set_kernel_path(300 + CHAIN_MASK_DEFAULT)
 
 
-CHAIN_MASK_DEFAULT = 15
+CHAIN_MASK_DEFAULT = 31
 
 
 def _chained_gs_checks(grid, Ni, Nj, L):
