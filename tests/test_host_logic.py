@@ -111,3 +111,26 @@ def test_mms_fields_host():
     X, Y = np.meshgrid(np.linspace(-1, 1, 7), np.linspace(-1, 1, 5))
     assert np.array_equal(m.solution(X, Y), o.solution(X, Y))
     assert np.array_equal(m.source(X, Y), o.source(X, Y))
+
+
+def test_full_size_config_generators_follow_the_shipped_grid_rule():
+    """tools/bench_configs.py and bench.py generate the C3/C4 grids with their own code (the product side may
+    not import the oracle); they must agree with the oracle's restatement of the shipped grids' rule."""
+    import importlib.util
+    import os
+    import sys
+    from dgoracle import plot3d
+    from helpers import REPO
+    import bench
+    x, y = plot3d.rectangle_nodes(6, 6, 2)
+    xn, yn = bench.rectangle_nodes_file_order(6, 2)
+    assert np.array_equal(xn, x.T) and np.array_equal(yn, y.T)
+    # bench_configs imports torch-only product modules at import time; load just its generator
+    src = open(os.path.join(REPO, "tools", "bench_configs.py")).read()
+    ns = {}
+    start = src.index("def lgl_line")
+    end = src.index("def timed")
+    exec("import numpy as np\nfrom dg_multigrid_solver_b200.tables import gauss_lobatto_nodes\n" + src[start:end], ns)
+    xc, yc = plot3d.circle_in_circle_nodes(8, 8, 3)
+    xg, yg = ns["circle_nodes_file_order"](8, 3)
+    assert np.allclose(xg, xc.T, rtol=0, atol=1e-15) and np.allclose(yg, yc.T, rtol=0, atol=1e-15)
