@@ -92,8 +92,11 @@ typedef struct dgb_operator {
 #define DGB_FLAG_GHOST_LO 8
 #define DGB_FLAG_GHOST_HI 16
 
-/* 0 = auto (streaming kernels where the operator allows), 1 = generic kernels only.
- * Returns the previous setting. */
+/* 0 = auto (single-launch smoother kernels where the operator allows), 1 = generic kernels only.
+ * Tuning values (tests and probes): 100+v experiment switch of the smoother kernels, 200+b smallest block
+ * size for the TMA-staged apply kernel (off by default), 300+mask block sizes the chained Gauss-Seidel kernel is
+ * used for (bit 0..4 = b 4, 9, 16, 25, 36; default all), 400+n CTAs per thread-block cluster of that kernel.
+ * Returns the previous setting of the 0/1 switch. */
 int dgb_set_kernel_path(int32_t path);
 /* Error flag of the asynchronous kernels (0 ok, 1 = TMA/mbarrier wait timed out, 2 = row
  * dependency wait timed out).  Synchronises the device. */
