@@ -13,6 +13,9 @@
  *     without synchronising, unless documented otherwise;
  *   - return value: 0 = ok, <0 = CUDA/launch error (dgb_last_error() has the text),
  *     >0 = argument error;
+ *   - one process drives one GPU from one thread at a time (the reference is single-threaded): the
+ *     smoother kernels share a device-side ticket counter and error flag, so two smoother calls must
+ *     not run concurrently on different streams of the same process;
  *   - all reals are IEEE fp64, all indices int32 (scipy's default index type, which the
  *     reference's sp.bsr_array uses);
  *   - BSR layout is scipy's: data[nnzb][b][b] row-major blocks, indices[nnzb] ascending
