@@ -623,7 +623,6 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
     __shared__ int s_ticket;
     double *stages = reinterpret_cast<double *>(smem);
     double *rings = reinterpret_cast<double *>(smem + C::o_ring(W));
-    double *scratch = reinterpret_cast<double *>(smem + C::o_scr(W));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::o_bar(W));
     volatile int *s_prog = reinterpret_cast<volatile int *>(smem + C::o_prog(W));
     double *xfirst = reinterpret_cast<double *>(smem + ((BigCfg<B>::o_xf(W) + 15) & ~(size_t)15));
@@ -709,7 +708,7 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
     };
     if (pred == 2) mb_load(0);
 
-    const uint32_t in_b = smem_u32(inring), row_b = smem_u32(rowring), scr = smem_u32(scratch);
+    const uint32_t in_b = smem_u32(inring), row_b = smem_u32(rowring);
     const uint32_t out_b = (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank));
     const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
                                          : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
@@ -786,7 +785,6 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
                 __stcg(mbox + ((size_t)j * Ni + i) * B + 2 * q + 1, xn.y);
             }
         }
-        (void)scr;
         __syncwarp();
         if (lane == 0 && t + NS < Ni) {
             fence_proxy_async();
