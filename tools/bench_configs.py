@@ -93,7 +93,14 @@ def main():
         t3 = timed(lambda: smoother(3), reps=2)
         t_gs = (t3 - t1) / 2.0                       # one symmetric iteration inside a longer call
         t_gs_first = t1
+        # the reference's `-s --smoother block_gauss_seidel_pyamg` run: 100 symmetric iterations with residual tests
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d.solver.solve()
+        torch.cuda.synchronize()
+        t_s100 = time.perf_counter() - t0
         out = {"config": f"C4 CircleInCircle {n}x{n} p=5 O-grid", "elements": N, "dofs": N * b, "b": b, "nnzb": nnzb,
+               "smoother_run_100_iterations_s": t_s100,
                "operator_GB": nnzb * b * b * 8 / 1e9, "setup_s": setup, "assemble_s": d.timings.get("assemble"),
                "assembly_elements_per_s": N / d.timings["assemble"],
                "apply_ms": t_apply, "apply_GBs": ab["apply"] / t_apply / 1e6, "apply_frac": ab["apply"] / t_apply / 1e6 / peak,
