@@ -40,12 +40,13 @@ class Level(ctypes.Structure):
                 ("transfer_kind", c_i32), ("nc", c_i32), ("nf", c_i32), ("pad0", c_i32),
                 ("R", c_vp), ("P", c_vp),
                 ("smoother", c_i32), ("direction", c_i32),
-                ("pre_iterations", c_i32), ("post_iterations", c_i32), ("omega", c_f64)]
+                ("pre_iterations", c_i32), ("post_iterations", c_i32), ("omega", c_f64),
+                ("post_smoother", c_i32), ("post_direction", c_i32), ("post_omega", c_f64)]
 
 
 class VcycleOpts(ctypes.Structure):
     _fields_ = [("gs_mode", c_i32), ("check_residual", c_i32), ("coarse_iterations", c_i32),
-                ("reserved", c_i32), ("u_final_event", c_vp)]
+                ("coarse_solver", c_i32), ("u_final_event", c_vp), ("coarse_inverse", c_vp)]
 
 
 class TablesDesc(ctypes.Structure):
@@ -59,6 +60,7 @@ TRANSFER_P, TRANSFER_H = 1, 2
 SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_seidel": 2}
 FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV, FLAG_GHOST_LO, FLAG_GHOST_HI = 1, 2, 4, 8, 16
 UNSUPPORTED = 100        # DGB_UNSUPPORTED
+COARSE_SMOOTHER, COARSE_DIRECT = 0, 1
 
 # name -> (restype, argtypes); every symbol include/dgb200.h declares
 OP = ctypes.POINTER(Operator)
@@ -70,6 +72,9 @@ SIGNATURES = {
     "dgb_launch_count": (ctypes.c_longlong, [c_i32]),
     "dgb_set_kernel_path": (c_i32, [c_i32]),
     "dgb_device_error": (c_i32, [c_i32]),
+    "dgb_fill_sentinel": (c_i32, [c_vp, c_i64, c_vp]),
+    "dgb_dense_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_dense_solve": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     "dgb_bsr_apply": (c_i32, [OP, c_vp, c_vp, c_vp]),
     "dgb_bsr_residual": (c_i32, [OP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -118,7 +123,7 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.dgb_abi_version() != 4:
+    if L.dgb_abi_version() != 5:
         raise DgbError("libdgb200.so ABI version mismatch")
     if os.environ.get("DGB_KERNELS", "auto") == "generic":
         L.dgb_set_kernel_path(1)
@@ -163,6 +168,21 @@ def call(name, *args):
     rc = getattr(L, name)(*conv)
     check(rc, name)
     return rc
+
+
+def check_device_error(mailboxes=()):
+    """Read (and reset) the error flag of the asynchronous smoother kernels wherever the host already
+    synchronises.  A non-zero flag means a bounded wait timed out and a pass returned early: the mailboxes
+    are refilled with the sentinel so that a later pass starts clean, and the solve is reported as failed."""
+    L = load()
+    err = L.dgb_device_error(1)
+    if err:
+        for m in mailboxes:
+            if m is not None:
+                call("dgb_fill_sentinel", m, int(m.numel()), stream_ptr())
+        raise DgbError(f"a lexicographic Gauss-Seidel kernel timed out on the device (dgb_device_error={err}: "
+                       "1 = TMA/mbarrier wait, 2 = row hand-over wait); the iterate is partly updated -- "
+                       "results of this solve are invalid (GPU time-sliced or stalled under a profiler?)")
 
 
 def require_cuda():

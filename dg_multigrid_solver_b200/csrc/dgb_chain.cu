@@ -193,9 +193,6 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32
 __device__ __forceinline__ void sts1_cluster(uint32_t a, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
-__device__ __forceinline__ void sts_cluster_u32(uint32_t a, int v) {
-    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
 __device__ __forceinline__ int ldv_cluster_s32(uint32_t a) {
     int v;
     asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -270,10 +267,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     // one ticket per cluster: the CTAs of a cluster take consecutive groups of W bands and hand their last row
     // over through distributed shared memory; only the last CTA of a cluster uses the global mailbox
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-    if (crank == 0 && threadIdx.x == 0) {
-        const int tk = atomicAdd(&work[0], 1);
-        for (uint32_t c = 0; c < csize; ++c) sts_cluster_u32(cluster_map(smem_u32(&s_ticket), c), tk);
-    }
+    if (crank == 0 && threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
     if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
     // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
     for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
@@ -283,12 +277,14 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
         fence_barrier_init();
         fence_proxy_async();
     }
-    cluster_sync_all();            // rings initialised and the ticket delivered in every CTA of the cluster
+    cluster_sync_all();            // rings initialised in every CTA of the cluster, rank 0 holds the ticket
+    const int ticket = ldv_cluster_s32(cluster_map(smem_u32(&s_ticket), 0));
+    cluster_sync_all();            // rank 0 may not leave before everybody has read its shared memory
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(w));
     asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
-    const int band = (s_ticket * (int)csize + (int)crank) * W + w;
+    const int band = (ticket * (int)csize + (int)crank) * W + w;
     const int sr0 = band * R;                      // first row of the band, in sweep order
     if (sr0 >= nrows) return;
     const int Rv = min(R, nrows - sr0);            // rows of this band
@@ -628,10 +624,7 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
     double *xfirst = reinterpret_cast<double *>(smem + ((BigCfg<B>::o_xf(W) + 15) & ~(size_t)15));
     const double sentinel = __longlong_as_double(-1LL);
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-    if (crank == 0 && threadIdx.x == 0) {
-        const int tk = atomicAdd(&work[0], 1);
-        for (uint32_t c = 0; c < csize; ++c) sts_cluster_u32(cluster_map(smem_u32(&s_ticket), c), tk);
-    }
+    if (crank == 0 && threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
     if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
     for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
     if ((threadIdx.x & 31) == 0) {
@@ -641,11 +634,13 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
         fence_proxy_async();
     }
     cluster_sync_all();
+    const int ticket = ldv_cluster_s32(cluster_map(smem_u32(&s_ticket), 0));
+    cluster_sync_all();
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(w));
     asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
-    const int sr = (s_ticket * (int)csize + (int)crank) * W + w;       // my row, in sweep order
+    const int sr = (ticket * (int)csize + (int)crank) * W + w;       // my row, in sweep order
     if (sr >= nrows) return;
     uint64_t *full = bars + w * NS;
     const int q = lane % LPL;                        // lanes >= LPL shadow the first ones (they never store)

@@ -1,6 +1,6 @@
-// dgb_solve.cu -- solve-phase kernels (apply / residual / smoothers / transfers), generic
-// row-per-thread versions.  These are the always-available path for any BSR structure; the
-// TMA-pipelined streaming kernels in dgb_stream.cu take over for the hot configurations.
+// dgb_solve.cu -- solve-phase kernels (apply / residual / smoothers / transfers): row-per-thread
+// streaming kernels for any BSR structure; the lexicographic Gauss-Seidel order runs in the single-launch
+// kernels of dgb_chain.cu / dgb_stream.cu where the operator has the DG 5-point stencil.
 //
 // Reference semantics restated here:
 //   y = A x            scipy bsr_matvec               <- dgfem/solver.py:117,119,150
@@ -190,8 +190,7 @@ static int rows_grid(int count, int epb, int occ = 8) {
 __global__ void k_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, double n) {
     ctl->res0 = sqrt(*sumsq / n);
     ctl->ratio = 1.0;
-    ctl->skip = 0;
-    ctl->diverged = 0;
+    ctl->skip = ctl->diverged;      // `diverged` is sticky (only the host clears it): nothing runs after a divergence
     ctl->iters = 0;
     ctl->calls += 1;
 }
@@ -388,16 +387,11 @@ k_prolong_add(int kind, const double *__restrict__ P, int nc, int nf, int Nj_c, 
 }  // namespace dgb
 
 namespace dgb {
-// streaming kernels (dgb_stream.cu)
+// single-launch lexicographic smoother kernels (dgb_stream.cu, dgb_chain.cu)
 extern int g_kernel_path;
-extern int g_kstream_min_b;
 bool stream_supported(int b);
-int stream_launch(int mode, int b, const double *data, const int32_t *indices, const int32_t *indptr, int N,
-                  int Ni, const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
-                  int colour, const int32_t *skip, cudaStream_t st, int *grid_out);
 int gs_rows_launch(int b, const double *gs, const double *rhs, double *x, double *mbox, int Ni, int Nj, int flags,
                    int dir, double omega, const int32_t *skip, cudaStream_t st);
-enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
 // chained lexicographic GS (dgb_chain.cu)
 bool chain_supported(int b, int flags);
 int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir, bool have_c, const int32_t *skip,
@@ -410,10 +404,6 @@ int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const do
 static bool use_stream(const dgb_operator *op) {
     return g_kernel_path == 0 && op->stencil >= 0 && stream_supported(op->b);
 }
-// k_stream (apply / residual / Jacobi / colour sweeps): measured on B200 the row-per-thread kernels win for
-// small blocks (b <= 9: their strided row reads are still served by the L1; profiles/r01_probe1_*.jsonl),
-// the TMA-staged kernel for the larger ones
-static bool use_kstream(const dgb_operator *op) { return use_stream(op) && op->b >= g_kstream_min_b; }
 static int check_op(const dgb_operator *op) {
     DGB_ARG(op != nullptr);
     DGB_ARG(op->data && op->indices && op->indptr && op->Ni > 0 && op->Nj > 0 && op->b > 0);
@@ -509,9 +499,6 @@ int dgb_bsr_apply(const dgb_operator *op, const double *x, double *y, void *stre
     DGB_ARG(x && y);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
-    if (use_kstream(op))
-        return stream_launch(S_APPLY, op->b, op->data, op->indices, op->indptr, N, op->Ni, nullptr, x, y, nullptr,
-                             1.0, -1, nullptr, st, nullptr);
     Sel sel{0, 0, N, 1, 0, N};
     DGB_DISPATCH_B(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_APPLY>()), RowCfg<B>::NT, 0, st>>>(
                               op->data, op->indices, op->indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
@@ -527,17 +514,11 @@ int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x,
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     int grid = 1;
-    if (use_kstream(op)) {
-        rc = stream_launch(S_RESIDUAL, op->b, op->data, op->indices, op->indptr, N, op->Ni, rhs, x, r, partials, 1.0,
-                           -1, skip, st, &grid);
-        if (rc) return rc;
-    } else {
-        Sel sel{0, 0, N, 1, 0, N};
-        DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
-                       k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
-                           op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
-        DGB_LAUNCH_OK();
-    }
+    Sel sel{0, 0, N, 1, 0, N};
+    DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
+                   k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
+                       op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
+    DGB_LAUNCH_OK();
     k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
     DGB_LAUNCH_OK();
     return 0;
@@ -627,13 +608,8 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
-            if (use_kstream(op) && op->gs_data != nullptr) {
-                rc = stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x, x, nullptr,
-                                   1.0, colour, skip, st, nullptr);
-            } else {
-                Sel sel{1, colour, op->Ni, op->Nj, 0, N};
-                rc = relax_launch(op, rhs, x, x, 1.0, sel, skip, st);
-            }
+            Sel sel{1, colour, op->Ni, op->Nj, 0, N};
+            rc = relax_launch(op, rhs, x, x, 1.0, sel, skip, st);
             if (rc) return rc;
         }
         return 0;
@@ -685,9 +661,6 @@ int dgb_block_relax_sweep(const dgb_operator *op, const double *rhs, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     if (x_in == x_out) return lexicographic_pass(op, rhs, x_out, omega, +1, nullptr, st);
-    if (use_kstream(op) && op->gs_data != nullptr)
-        return stream_launch(S_RELAX, op->b, op->gs_data, op->indices, op->indptr, N, op->Ni, rhs, x_in, x_out,
-                             nullptr, omega, -1, nullptr, st, nullptr);
     Sel sel{0, 0, op->Ni, op->Nj, 0, N};
     return relax_launch(op, rhs, x_in, x_out, omega, sel, nullptr, st);
 }

@@ -1,53 +1,22 @@
-// dgb_stream.cu -- the HBM-streaming kernels of the V-cycle, sm_100a.
+// dgb_stream.cu -- the row-pipelined lexicographic block Gauss-Seidel kernel, sm_100a, and the device-side
+// bookkeeping (ticket / error words) shared by the single-launch smoother kernels.
 //
-//  k_stream<B,MODE>  persistent CTAs; one producer warp feeds a ring of shared-memory stages with
-//                    TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of whole block rows,
-//                    eight consumer warps do block-row x vector products out of shared memory.
-//                    MODE: apply y=Ax | residual r=b-Ax with fused sum(r^2) | relaxation
-//                    (block-Jacobi, or one colour of the red-black block-GS, in place).
 //  k_gs_rows<B>      lexicographic block Gauss-Seidel, exact sweep order: one warp per element
-//                    row j, rows pipelined against each other through release/acquire progress
-//                    counters in global memory (row j may process element i once row j-1 has
+//                    row j, rows pipelined against each other (row j may process element i once row j-1 has
 //                    finished element i); each warp streams its row's blocks through its own
 //                    TMA-fed ring.  CTAs take tickets so that a CTA only ever waits on CTAs
-//                    that were started before it.
+//                    that were started before it.  Used where the chained kernel (dgb_chain.cu) does not
+//                    apply: grids periodic in j, b = 25 on O-grids, omega != 1.
 //
-// Reference semantics: scipy bsr_matvec (dgfem/solver.py:117,119,150), pyamg
-// amg_core.block_gauss_seidel (dgfem/pyamg_relaxation.py:252-255), dgfem/relaxation.py:123-195.
-// The smoother kernels read the "GS stream": the BSR data with each diagonal block replaced by
-// its inverse (dgb_build_gs_stream), so one pass reads exactly nnzb blocks.
+// Reference semantics: pyamg amg_core.block_gauss_seidel (dgfem/pyamg_relaxation.py:252-255),
+// dgfem/relaxation.py:170-195.  The kernel reads the "GS stream": the BSR data with each diagonal block
+// replaced by its inverse (dgb_build_gs_stream), so one pass reads exactly nnzb blocks.
 #include "dgb_async.cuh"
 #include "dgb_common.cuh"
 
 namespace dgb {
 
 constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
-
-enum { S_APPLY = 0, S_RESIDUAL = 1, S_RELAX = 2 };
-
-// =========================================================================================
-// k_stream
-// =========================================================================================
-template <int B>
-struct StreamCfg {
-    static constexpr int B2 = B * B;
-    static constexpr int T = B <= 4 ? 32 : B <= 9 ? 8 : B <= 16 ? 4 : B <= 25 ? 2 : 1;   // block rows per stage
-    static constexpr int S = B <= 4 ? 4 : 3;                                            // stages
-    static constexpr int MAXBR = 5;                                                     // blocks per row
-    static constexpr int ROWSLOT = (MAXBR * B2 + 2 + 1) & ~1;                            // doubles, even
-    static constexpr int STAGE_D = T * ROWSLOT;
-    static constexpr int NCW = 8, NC = NCW * 32, NT = NC + 32;
-    static constexpr int PD = 16 / gcd_c(B, 16);          // period of (B*t mod 16): bank skew, see below
-    // dynamic shared memory layout (bytes)
-    static constexpr size_t oStage = 0;
-    static constexpr size_t oPartial = oStage + sizeof(double) * S * STAGE_D;
-    static constexpr size_t oRsum = oPartial + sizeof(double) * 2 * T * MAXBR * B;
-    static constexpr size_t oBar = oRsum + sizeof(double) * 2 * T * B;                   // full[S], empty[S]
-    static constexpr size_t oInts = oBar + sizeof(uint64_t) * 2 * S;
-    // ints: row_off[S][T], row_n[S][T], row_cix[S][T], cols[S][T*MAXBR], diag_t[2][T]
-    static constexpr size_t nInts = 3 * S * T + S * T * MAXBR + 2 * T;
-    static constexpr size_t SMEM = oInts + sizeof(int) * nInts;
-};
 
 // Skewed column order: item t (consecutive items <-> consecutive lanes) reads row t of a B-wide
 // row-major block from shared memory; rows are B doubles apart, so without a skew lanes t and
@@ -63,184 +32,6 @@ __device__ __forceinline__ double skew_dot(const double *__restrict__ a, const d
         acc = fma(a[cc], v[cc], acc);
     }
     return acc;
-}
-
-template <int B, int MODE>
-__global__ void __launch_bounds__(StreamCfg<B>::NT)
-k_stream(const double *__restrict__ data, const int32_t *__restrict__ indices,
-         const int32_t *__restrict__ indptr, int N, int Ni, const double *__restrict__ rhs,
-         const double *x_in, double *x_out, double *partials, double omega, int colour, int *err,
-         const int32_t *__restrict__ skip) {
-    using C = StreamCfg<B>;
-    constexpr int T = C::T, S = C::S, B2 = C::B2, NC = C::NC, MAXBR = C::MAXBR;
-    if (skip != nullptr && *skip != 0) return;
-    extern __shared__ __align__(128) unsigned char smem[];
-    double *stage = reinterpret_cast<double *>(smem + C::oStage);
-    double *partial = reinterpret_cast<double *>(smem + C::oPartial);
-    double *rsum = reinterpret_cast<double *>(smem + C::oRsum);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::oBar);
-    uint64_t *empty = full + S;
-    int *row_off = reinterpret_cast<int *>(smem + C::oInts);
-    int *row_n = row_off + S * T;
-    int *row_cix = row_n + S * T;
-    int *cols = row_cix + S * T;
-    int *diag_t = cols + S * T * MAXBR;
-    __shared__ double s_red[C::NCW];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], C::NCW);
-        }
-        fence_barrier_init();
-        fence_proxy_async();
-    }
-    __syncthreads();
-    const int ntiles = (N + T - 1) / T;
-
-    if (warp == 0) {
-        // ------------------------------- producer warp ------------------------------------
-        const char *gbytes = reinterpret_cast<const char *>(data);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            bool ok = true;
-            if (lane == 0) ok = mbar_wait(&empty[s], ph ^ 1, err);
-            ok = __shfl_sync(0xffffffffu, ok, 0);
-            if (!ok) return;
-            const int e0 = tile * T;
-            const int nrow = min(T, N - e0);
-            int ip_lo = 0, ip_hi = 0;
-            if (lane < nrow) {
-                ip_lo = indptr[e0 + lane];
-                ip_hi = indptr[e0 + lane + 1];
-            }
-            double *sbase = stage + (size_t)s * C::STAGE_D;
-            if (colour < 0) {
-                // one bulk copy for the whole tile (its blocks are contiguous in the BSR data)
-                const int k0 = __shfl_sync(0xffffffffu, ip_lo, 0);
-                const int k1 = __shfl_sync(0xffffffffu, ip_hi, nrow - 1);
-                const size_t byte0 = (size_t)k0 * B2 * 8, byte1 = (size_t)k1 * B2 * 8;
-                const size_t a0 = byte0 & ~(size_t)15, a1 = (byte1 + 15) & ~(size_t)15;
-                const int shift = (int)((byte0 - a0) >> 3);
-                if (lane < T) {
-                    row_off[s * T + lane] = lane < nrow ? (ip_lo - k0) * B2 + shift : 0;
-                    row_n[s * T + lane] = lane < nrow ? ip_hi - ip_lo : 0;
-                    row_cix[s * T + lane] = ip_lo - k0;
-                }
-                for (int k = lane; k < k1 - k0; k += 32) cols[s * T * MAXBR + k] = indices[k0 + k];
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_expect_tx(&full[s], (uint32_t)(a1 - a0));
-                    bulk_g2s(sbase, gbytes + a0, (uint32_t)(a1 - a0), &full[s]);
-                }
-            } else {
-                // one colour class: one bulk copy per active block row into its own slot
-                const int e = e0 + lane;
-                const bool active = lane < nrow && ((((e % Ni) + (e / Ni)) & 1) == colour);
-                const int nb = active ? ip_hi - ip_lo : 0;
-                const size_t byte0 = (size_t)ip_lo * B2 * 8, byte1 = (size_t)ip_hi * B2 * 8;
-                const size_t a0 = byte0 & ~(size_t)15, a1 = (byte1 + 15) & ~(size_t)15;
-                const int shift = (int)((byte0 - a0) >> 3);
-                uint32_t bytes = active ? (uint32_t)(a1 - a0) : 0u;
-                if (lane < T) {
-                    row_off[s * T + lane] = lane * C::ROWSLOT + shift;
-                    row_n[s * T + lane] = nb;
-                    row_cix[s * T + lane] = lane * MAXBR;
-                }
-                for (int t = 0; t < nb; ++t) cols[s * T * MAXBR + lane * MAXBR + t] = indices[ip_lo + t];
-                uint32_t total = bytes;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                __syncwarp();
-                if (lane == 0) mbar_expect_tx(&full[s], total);
-                __syncwarp();
-                if (active) bulk_g2s(sbase + (size_t)lane * C::ROWSLOT, gbytes + a0, bytes, &full[s]);
-            }
-        }
-        return;
-    }
-
-    // ----------------------------------- consumer warps -------------------------------------
-    const int ctid = tid - 32;
-    const int q = (ctid & 15) / C::PD;
-    double sumsq = 0.0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        if (!mbar_wait(&full[s], ph, err)) return;
-        const int e0 = tile * T;
-        const int nrow = min(T, N - e0);
-        const double *st = stage + (size_t)s * C::STAGE_D;
-        const int pb = it & 1;
-        double *part = partial + (size_t)pb * T * MAXBR * B;
-        double *rs = rsum + (size_t)pb * T * B;
-        // phase 1: one item = (row l, block t, scalar row r): dot of one block row with x[col]
-        for (int item = ctid; item < nrow * MAXBR * B; item += NC) {
-            const int l = item / (MAXBR * B);
-            const int rem = item - l * (MAXBR * B);
-            const int t = rem / B, r = rem - t * B;
-            if (t < row_n[s * T + l]) {
-                const int e = e0 + l;
-                const int col = cols[s * T * MAXBR + row_cix[s * T + l] + t];
-                double acc = 0.0;
-                if (MODE == S_RELAX && col == e) {
-                    if (r == 0) diag_t[pb * T + l] = t;
-                } else {
-                    acc = skew_dot<B>(st + row_off[s * T + l] + t * B2 + r * B, x_in + (size_t)col * B, q);
-                }
-                part[item] = acc;
-            }
-        }
-        named_bar_sync<1, NC>();
-        // phase 2: sum the row's blocks in stored (ascending column) order
-        for (int item = ctid; item < nrow * B; item += NC) {
-            const int l = item / B, r = item - l * B;
-            const int n = row_n[s * T + l];
-            if (n > 0) {
-                double acc = 0.0;
-                for (int t = 0; t < n; ++t) acc += part[(l * MAXBR + t) * B + r];
-                const size_t o = (size_t)(e0 + l) * B + r;
-                if (MODE == S_APPLY) {
-                    x_out[o] = acc;
-                } else if (MODE == S_RESIDUAL) {
-                    const double res = rhs[o] - acc;
-                    if (x_out != nullptr) x_out[o] = res;
-                    sumsq = fma(res, res, sumsq);
-                } else {
-                    rs[item] = rhs[o] - acc;
-                }
-            }
-        }
-        if (MODE == S_RELAX) {
-            named_bar_sync<1, NC>();
-            // phase 3: x_i = omega * Dinv_i * rsum_i + (1 - omega) * x_i
-            for (int item = ctid; item < nrow * B; item += NC) {
-                const int l = item / B, r = item - l * B;
-                if (row_n[s * T + l] > 0) {
-                    const double *d = st + row_off[s * T + l] + diag_t[pb * T + l] * B2 + r * B;
-                    const double xn = skew_dot<B>(d, rs + l * B, q);
-                    const size_t o = (size_t)(e0 + l) * B + r;
-                    x_out[o] = (omega == 1.0) ? xn : omega * xn + (1.0 - omega) * x_in[o];
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-    }
-    if (MODE == S_RESIDUAL) {
-        sumsq = warp_sum(sumsq);
-        if (lane == 0) s_red[warp - 1] = sumsq;
-        named_bar_sync<1, NC>();
-        if (ctid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < C::NCW; ++w) t += s_red[w];
-            partials[blockIdx.x] = t;
-        }
-    }
 }
 
 // =========================================================================================
@@ -933,72 +724,42 @@ k_check_stencil(const int32_t *__restrict__ indices, const int32_t *__restrict__
 
 // ---------------------------------------------------------------------------------------
 // host side
-static int *g_work = nullptr;      // [0] ticket, [1..] progress
-static int g_work_cap = 0;
-static int *g_err = nullptr;       // device-side error flag of the async kernels
-int g_kernel_path = 0;             // 0 auto (streaming kernels where available), 1 generic only
-int g_kstream_min_b = 1000;        // k_stream v1 loses to the row-per-thread kernels for every b measured (profiles/r01_probe10); off by default (tuning: dgb_set_kernel_path(200 + b))
+// ticket word and error flag of the single-launch smoother kernels: one pair per device, allocated on first
+// use on that device.  The ticket is reset (stream-ordered) before every launch, so smoother launches of one
+// device must be issued on one stream at a time (include/dgb200.h, "Conventions").
+constexpr int kMaxDevices = 64;
+struct DevState {
+    int *work = nullptr;   // [0] ticket
+    int *err = nullptr;    // device-side error flag of the asynchronous kernels
+};
+static DevState g_dev[kMaxDevices];
+int g_kernel_path = 0;             // 0 auto (single-launch smoother kernels where available), 1 generic only
 
-int *work_ptr() { return g_work; }
-int *err_ptr() { return g_err; }
-int ensure_work(int n_rows) {
-    if (g_err == nullptr) {
-        DGB_CUDA_OK(cudaMalloc(&g_err, sizeof(int)));
-        DGB_CUDA_OK(cudaMemset(g_err, 0, sizeof(int)));
+static DevState *dev_state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_dev[dev];
+}
+int *work_ptr() { DevState *d = dev_state(); return d ? d->work : nullptr; }
+int *err_ptr() { DevState *d = dev_state(); return d ? d->err : nullptr; }
+int ensure_work(int) {
+    DevState *d = dev_state();
+    if (d == nullptr) {
+        set_error("ensure_work: no current CUDA device");
+        return -1;
     }
-    if (n_rows + 2 > g_work_cap) {
-        if (g_work) cudaFree(g_work);
-        g_work_cap = n_rows + 2 + 4096;
-        DGB_CUDA_OK(cudaMalloc(&g_work, sizeof(int) * g_work_cap));
+    if (d->err == nullptr) {
+        DGB_CUDA_OK(cudaMalloc(&d->err, sizeof(int)));
+        DGB_CUDA_OK(cudaMemset(d->err, 0, sizeof(int)));
+    }
+    if (d->work == nullptr) {
+        DGB_CUDA_OK(cudaMalloc(&d->work, sizeof(int) * 64));
+        DGB_CUDA_OK(cudaMemset(d->work, 0, sizeof(int) * 64));
     }
     return 0;
 }
 
 bool stream_supported(int b) { return b == 1 || b == 4 || b == 9 || b == 16 || b == 22 || b == 25 || b == 36; }
-
-template <int B, int MODE>
-static int stream_launch_t(const double *data, const int32_t *indices, const int32_t *indptr, int N, int Ni,
-                           const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
-                           int colour, const int32_t *skip, cudaStream_t st, int *grid_out) {
-    using C = StreamCfg<B>;
-    static bool configured = false;
-    static int occ = 1;
-    if (!configured) {
-        DGB_CUDA_OK(cudaFuncSetAttribute(k_stream<B, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        DGB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<B, MODE>, C::NT, C::SMEM));
-        if (occ < 1) occ = 1;
-        if (occ > 2) occ = 2;
-        configured = true;
-    }
-    const int ntiles = (N + C::T - 1) / C::T;
-    int grid = sm_count() * occ;
-    if (grid > ntiles) grid = ntiles;
-    if (grid > kMaxPartials) grid = kMaxPartials;
-    k_stream<B, MODE><<<grid, C::NT, C::SMEM, st>>>(data, indices, indptr, N, Ni, rhs, x_in, x_out, partials, omega,
-                                                   colour, g_err, skip);
-    DGB_LAUNCH_OK();
-    if (grid_out) *grid_out = grid;
-    return 0;
-}
-
-// mode: S_APPLY / S_RESIDUAL / S_RELAX
-int stream_launch(int mode, int b, const double *data, const int32_t *indices, const int32_t *indptr, int N,
-                  int Ni, const double *rhs, const double *x_in, double *x_out, double *partials, double omega,
-                  int colour, const int32_t *skip, cudaStream_t st, int *grid_out) {
-    int rc = ensure_work(0);
-    if (rc) return rc;
-    if (mode == S_APPLY) {
-        DGB_DISPATCH_B(b, return (stream_launch_t<B, S_APPLY>(data, indices, indptr, N, Ni, rhs, x_in, x_out, partials,
-                                                             omega, colour, skip, st, grid_out)));
-    } else if (mode == S_RESIDUAL) {
-        DGB_DISPATCH_B(b, return (stream_launch_t<B, S_RESIDUAL>(data, indices, indptr, N, Ni, rhs, x_in, x_out,
-                                                                partials, omega, colour, skip, st, grid_out)));
-    } else {
-        DGB_DISPATCH_B(b, return (stream_launch_t<B, S_RELAX>(data, indices, indptr, N, Ni, rhs, x_in, x_out, partials,
-                                                             omega, colour, skip, st, grid_out)));
-    }
-    return 0;
-}
 
 template <int B, int WW, int SS>
 static int gs_rows_launch_c(const double *gs, const double *rhs, double *x, double *mbox, Stencil S_, int dir,
@@ -1010,9 +771,9 @@ static int gs_rows_launch_c(const double *gs, const double *rhs, double *x, doub
                                          (int)C::SMEM));
         configured = true;
     }
-    DGB_CUDA_OK(cudaMemsetAsync(g_work, 0, sizeof(int), st));
+    DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
     const int grid = (S_.ja1 - S_.ja0 + C::W - 1) / C::W;
-    k_gs_rows<B, WW, SS><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, g_work, g_err, skip);
+    k_gs_rows<B, WW, SS><<<grid, C::W * 32, C::SMEM, st>>>(gs, rhs, x, mbox, S_, dir, omega, work_ptr(), err_ptr(), skip);
     DGB_LAUNCH_OK();
     return 0;
 }
@@ -1046,17 +807,17 @@ int dgb_set_kernel_path(int32_t path) {
     const int old = g_kernel_path;
     if (path == 0 || path == 1) g_kernel_path = path;
     if (path >= 100 && path < 200) g_gs_variant = path - 100;      // tuning experiments only
-    if (path >= 200 && path < 300) g_kstream_min_b = path - 200;
     if (path >= 300 && path < 332) g_chain_mask = path - 300;      // block sizes of the chained GS kernel
     if (path >= 400 && path <= 408) g_chain_cluster = path - 400;  // CTAs per cluster of the chained GS kernel
     return old;
 }
 
 int dgb_device_error(int32_t reset) {
-    if (g_err == nullptr) return 0;
+    int *err = err_ptr();
+    if (err == nullptr) return 0;
     int v = 0;
-    if (cudaMemcpy(&v, g_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    if (reset && v != 0) cudaMemset(g_err, 0, sizeof(int));
+    if (cudaMemcpy(&v, err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset && v != 0) cudaMemset(err, 0, sizeof(int));
     return v;
 }
 

@@ -10,31 +10,33 @@
 namespace dgb {
 
 // *have_residual (optional, out): L.r holds rhs - A u of the returned u (the smoother's own last residual test)
-static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream, bool *have_residual = nullptr,
-                  void *u_final_event = nullptr) {
+// (smoother, direction, omega): the pre- or the post-smoother's settings, resolved independently
+// (dgfem/solver.py:143-147,196)
+static int smooth(const dgb_level &L, int smoother, int direction, double omega, const dgb_vcycle_opts &o,
+                  int iterations, dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream,
+                  bool *have_residual = nullptr, void *u_final_event = nullptr) {
     if (have_residual) *have_residual = false;
-    if (iterations <= 0 || L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG) {
+    if (iterations <= 0 || smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG) {
         // no in-smoother hook: the event is recorded by the caller after the smoother returns
         if (u_final_event != nullptr && iterations <= 0)
             DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)u_final_event, (cudaStream_t)stream));
     }
     if (iterations <= 0) return 0;
     const size_t nbytes = sizeof(double) * (size_t)L.op.Ni * L.op.Nj * L.op.b;
-    switch (L.smoother) {
+    switch (smoother) {
     case DGB_SMOOTHER_BLOCK_GS_PYAMG:
         if (have_residual && o.check_residual) {
             *have_residual = true;
-            return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream);
+            return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream);
         }
-        return gs_pyamg(&L.op, L.rhs, L.u, L.direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
+        return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
                         nullptr, stream, u_final_event);
     case DGB_SMOOTHER_BLOCK_JACOBI: {
         // relaxation.py:123-150: iteration 1 is Jacobi into a fresh buffer, then `u = u_new`
         // aliases the two, so the remaining iterations are in-place forward sweeps.
-        int rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.r, L.omega, stream);
+        int rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.r, omega, stream);
         for (int it = 1; it < iterations && rc == 0; ++it)
-            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.r, L.r, L.omega, stream);
+            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.r, L.r, omega, stream);
         if (rc) return rc;
         DGB_CUDA_OK(cudaMemcpyAsync(L.u, L.r, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return 0;
@@ -42,11 +44,11 @@ static int smooth(const dgb_level &L, const dgb_vcycle_opts &o, int iterations, 
     case DGB_SMOOTHER_BLOCK_GS: {
         int rc = 0;
         for (int it = 0; it < iterations && rc == 0; ++it)   // relaxation.py:170-195 (forward only)
-            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.u, L.omega, stream);
+            rc = dgb_block_relax_sweep(&L.op, L.rhs, L.u, L.u, omega, stream);
         return rc;
     }
     default:
-        set_error("unknown smoother id %d", L.smoother);
+        set_error("unknown smoother id %d", smoother);
         return 3;
     }
 }
@@ -57,15 +59,21 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     void *ev = top ? o.u_final_event : nullptr;
+    if (k == 0 && o.coarse_solver == DGB_COARSE_DIRECT) {   // solver.py:199-200
+        rc = dgb_dense_solve(o.coarse_inverse, L.op.Ni * L.op.Nj * L.op.b, L.rhs, L.u, stream);
+        if (rc == 0 && ev != nullptr) DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
+        return rc;
+    }
     if (k == 0) {   // solver.py:201-204
-        rc = smooth(L, o, o.coarse_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
+        rc = smooth(L, L.smoother, L.direction, L.omega, o, o.coarse_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
         if (rc == 0 && ev != nullptr && L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG)
             DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
         return rc;
     }
     const dgb_level &C = lv[k - 1];
     bool have_r = false;
-    if ((rc = smooth(L, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r))) return rc;
+    if ((rc = smooth(L, L.smoother, L.direction, L.omega, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r)))
+        return rc;
     // residual = RHS - BSR @ u (solver.py:150); the pre-smoother's last residual test already evaluated exactly
     // this vector (same kernel, same inputs), so it is not computed twice
     if (!have_r && (rc = dgb_bsr_residual(&L.op, L.rhs, L.u, L.r, partials, sumsq, nullptr, stream))) return rc;
@@ -73,8 +81,9 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.op.Ni * C.op.Nj * C.op.b, st));   // solver.py:171
     if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream))) return rc;
     if ((rc = dgb_prolong_add(C.transfer_kind, C.P, C.nc, C.nf, C.op.Ni, C.op.Nj, C.u, L.u, stream))) return rc;
-    rc = smooth(L, o, L.post_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
-    if (rc == 0 && ev != nullptr && L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG && L.post_iterations > 0)
+    rc = smooth(L, L.post_smoother, L.post_direction, L.post_omega, o, L.post_iterations, ctl + k, partials, sumsq,
+                stream, nullptr, ev);
+    if (rc == 0 && ev != nullptr && L.post_smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG && L.post_iterations > 0)
         DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
     return rc;
 }
@@ -84,6 +93,8 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
 extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
                           dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream) {
     DGB_ARG(h_levels && h_opts && ctl && partials && sumsq && nlevels >= 1);
+    DGB_ARG(h_opts->coarse_solver == DGB_COARSE_SMOOTHER ||
+            (h_opts->coarse_solver == DGB_COARSE_DIRECT && h_opts->coarse_inverse != nullptr));
     for (int k = 0; k < nlevels; ++k) {
         const dgb_level &L = h_levels[k];
         DGB_ARG(L.op.data && L.op.indices && L.op.indptr && L.op.dinv && L.rhs && L.u && L.r);

@@ -82,20 +82,32 @@ class Relaxation:
         if check_residual is not None:
             chk = 1 if check_residual else 0
         _ensure_dinv(grid)
+        ws.ctl.zero_()                 # `diverged` is sticky on the device: every call starts from a clean block
         _lib.call("dgb_block_gauss_seidel_pyamg", grid.operator(), d_rhs, d_u, _DIRECTION[direction],
                   int(max_iterations), mode, chk, ws.ctl, ws.partials, ws.sumsq, _lib.stream_ptr())
         if host:
-            check_dinv(grid)
-            if chk:
-                ctl = ws.read_ctl()
-                cls.last_info = {"iterations": ctl.iters, "ratio": ctl.ratio, "early_exit": bool(ctl.skip and not ctl.diverged)}
-                if ctl.diverged:
-                    print(f"diverging, residual={ctl.ratio:.6e}")      # relaxation.py:214-216
-                    raise SystemExit()
-                if ctl.skip:
-                    print(f"Residual reduced by 6 orders in {ctl.iters} sweeps")   # relaxation.py:212
+            cls.finish(grid, chk)
             return d_u.cpu().numpy()
+        # device tensors in, device tensor out: no host synchronisation here -- the caller runs
+        # Relaxation.finish(grid) where it synchronises (divergence / singular-block / kernel-error checks)
         return d_u
+
+    @classmethod
+    def finish(cls, grid, check_residual=True):
+        """The host-side checks of a smoother call (dgfem/relaxation.py:211-216 and the inverse of a singular
+        diagonal block raising in pyamg): divergence -> SystemExit, early exit -> the reference's message;
+        also the error flag of the asynchronous kernels.  Synchronises."""
+        ws = _Workspace.get()
+        check_dinv(grid)
+        _lib.check_device_error([getattr(grid, "d_mailbox", None)])
+        if check_residual:
+            ctl = ws.read_ctl()
+            cls.last_info = {"iterations": ctl.iters, "ratio": ctl.ratio, "early_exit": bool(ctl.skip and not ctl.diverged)}
+            if ctl.diverged:
+                print(f"diverging, residual={ctl.ratio:.6e}")      # relaxation.py:214-216
+                raise SystemExit()
+            if ctl.skip:
+                print(f"Residual reduced by 6 orders in {ctl.iters} sweeps")   # relaxation.py:212
 
     @classmethod
     def block_jacobi(cls, grid, RHS, u=None, direction=None, omega=1, max_iterations=1e3):
@@ -115,6 +127,7 @@ class Relaxation:
             d_u = d_new
         if host:
             check_dinv(grid)
+            _lib.check_device_error([getattr(grid, "d_mailbox", None)])
             return d_u.cpu().numpy()
         return d_u
 
@@ -129,6 +142,7 @@ class Relaxation:
             _lib.call("dgb_block_relax_sweep", op, d_rhs, d_u, d_u, float(omega), st)
         if host:
             check_dinv(grid)
+            _lib.check_device_error([getattr(grid, "d_mailbox", None)])
             return d_u.cpu().numpy()
         return d_u
 

@@ -43,6 +43,8 @@ class Solver:
         with Timer() as timer:
             if self.method == "smoother":
                 u = self.solve_smoother(reference_grid, reference_grid.RHS)
+            elif self.method == "direct":
+                u = self.solve_directly(reference_grid, reference_grid.RHS)          # dgfem/solver.py:33-35
             elif self.method == "multigrid":
                 RHS_0 = reference_grid.RHS
                 u_0 = np.zeros_like(RHS_0)
@@ -52,7 +54,7 @@ class Solver:
             else:
                 raise NotImplementedError(
                     f"solver method '{self.method}' is outside the B200 hot path (SURVEY.md section 2.1 row 10); "
-                    "use -m or -s")
+                    "use -m, -s or -d")
         self.timings["solve"] = timer.elapsed()
         return u
 
@@ -91,15 +93,19 @@ class Solver:
             # one; the coarsest level uses the first link's (dgfem/solver.py:143,202)
             kind = self.multigrid_type[k - 1] if k > 0 else (self.multigrid_type[0] if self.multigrid_type else "polynomial")
             blk = self._smoother_block(kind)
+            # pre- and post-smoother are resolved independently (dgfem/solver.py:143-147,196)
             pre, post = blk.pre_smoother, blk.post_smoother
-            if pre.smoother != post.smoother or pre.direction != post.direction:
-                raise NotImplementedError("pre and post smoother of a coarsening must be the same smoother/direction")
-            if pre.smoother not in _lib.SMOOTHER_IDS:
-                raise AttributeError(f"Relaxation has no accelerated smoother '{pre.smoother}'")
+            for sm in (pre, post):
+                if sm.smoother not in _lib.SMOOTHER_IDS:
+                    raise AttributeError(f"Relaxation has no accelerated smoother '{sm.smoother}'")
+            directions = {"symmetric": 0, "forward": 1, "backward": -1}
             L.smoother = _lib.SMOOTHER_IDS[pre.smoother]
-            L.direction = {"symmetric": 0, "forward": 1, "backward": -1}[pre.direction]
+            L.direction = directions[pre.direction]
             L.pre_iterations, L.post_iterations = int(pre.iterations), int(post.iterations)
             L.omega = float(pre.relaxation_factor)
+            L.post_smoother = _lib.SMOOTHER_IDS[post.smoother]
+            L.post_direction = directions[post.direction]
+            L.post_omega = float(post.relaxation_factor)
             if k < n - 1:
                 R = torch.from_numpy(np.ascontiguousarray(self.restriction_operators[k], dtype=np.float64)).cuda()
                 P = torch.from_numpy(np.ascontiguousarray(self.prolongation_operators[k], dtype=np.float64)).cuda()
@@ -115,17 +121,48 @@ class Solver:
                     L.transfer_kind = _lib.TRANSFER_P
                 else:
                     raise NotImplementedError(f"multigrid type '{kind_up}' is out of scope")
-        if s.solver.multigrid.coarse_grid_solver != "smoother":
-            raise NotImplementedError("only `coarse grid solver: smoother` runs on the device "
-                                      "(paramfile.yml:23; SURVEY.md section 8f-4)")
         opts = _lib.VcycleOpts(gs_mode=_lib.GS_REDBLACK if gs_mode == "redblack" else _lib.GS_LEXICOGRAPHIC,
-                               check_residual=1 if chk else 0, coarse_iterations=10, reserved=0)
+                               check_residual=1 if chk else 0, coarse_iterations=10,
+                               coarse_solver=_lib.COARSE_SMOOTHER)
+        coarse_inverse = None
+        coarse = s.solver.multigrid.coarse_grid_solver
+        if coarse == "direct":
+            # dgfem/solver.py:199-200: spsolve on the coarsest level -> dense inverse, once per hierarchy
+            coarse_inverse = self.coarse_direct_inverse(self.grids[0])
+            opts.coarse_solver = _lib.COARSE_DIRECT
+            opts.coarse_inverse = coarse_inverse.data_ptr()
+        elif coarse != "smoother":
+            raise NotImplementedError(f"coarse grid solver '{coarse}' is outside the B200 hot path "
+                                      "(paramfile.yml:23: 'smoother' and 'direct' run on the device)")
         ctl = torch.zeros(32 * n, dtype=torch.uint8, device="cuda")
         partials = torch.zeros(_lib.load().dgb_partials_len(), dtype=torch.float64, device="cuda")
         sumsq = torch.zeros(1, dtype=torch.float64, device="cuda")
         self._hier = dict(levels=levels, n=n, vecs=vecs, ops=ops, opts=opts, ctl=ctl, partials=partials, sumsq=sumsq,
-                          grids=list(self.grids))
+                          grids=list(self.grids), coarse_inverse=coarse_inverse)
         return self._hier
+
+    @staticmethod
+    def coarse_direct_inverse(grid):
+        """Dense inverse of a level's operator (dgb_dense_inverse): the device-side `solve_directly`."""
+        torch = _lib.require_cuda()
+        b = grid.d_data.shape[1]
+        N = grid.d_indptr.numel() - 1
+        inv = torch.empty((N * b, N * b), dtype=torch.float64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.call("dgb_dense_inverse", grid.d_data, grid.d_indices, grid.d_indptr, N, b, inv, info, _lib.stream_ptr())
+        bad = int(info.item())
+        if bad:
+            raise np.linalg.LinAlgError(f"coarse-grid operator is singular (zero pivot in column {bad - 1})")
+        return inv
+
+    def solve_directly(self, grid, RHS):
+        """dgfem/solver.py:56-59 (spsolve(grid.BSR.tocsr(), RHS)) on the device; meant for coarse levels."""
+        torch = _lib.require_cuda()
+        d_rhs, host = _to_device(RHS)
+        inv = self.coarse_direct_inverse(grid)
+        u = torch.empty_like(d_rhs)
+        _lib.call("dgb_dense_solve", inv, int(d_rhs.numel()), d_rhs, u, _lib.stream_ptr())
+        return u.cpu().numpy() if host else u
 
     def hierarchy(self):
         if self._hier is None or self._hier["grids"] != list(self.grids):
@@ -140,11 +177,16 @@ class Solver:
         _lib.check(rc, "dgb_vcycle")
 
     def _check_divergence(self):
+        """Host-side view of the device state, wherever the host synchronises anyway: the sticky `diverged`
+        flags of the smoother control blocks (dgfem/relaxation.py:214-216 exits the process there) and the
+        error flag of the asynchronous kernels."""
         H = self.hierarchy()
         raw = H["ctl"].cpu().numpy().tobytes()
+        _lib.check_device_error([g.d_mailbox for g in H["grids"]])
         for k in range(H["n"]):
             c = _lib.SmootherCtl.from_buffer_copy(raw[32 * k:32 * (k + 1)])
             if c.diverged:
+                H["ctl"].zero_()                                     # the flag is sticky on the device
                 print(f"diverging, residual={c.ratio:.6e}")          # dgfem/relaxation.py:214-216
                 raise SystemExit()
 
@@ -229,7 +271,7 @@ class Solver:
                     break
                 self._vcycle_device(levels)
                 n += 1
-        self._check_divergence()
+                self._check_divergence()          # the reference leaves at the first diverging smoother call
         self._pickle_residuals(fine)
         return u_k.cpu().numpy() if host else u_k.clone()
 

@@ -13,9 +13,10 @@
  *     without synchronising, unless documented otherwise;
  *   - return value: 0 = ok, <0 = CUDA/launch error (dgb_last_error() has the text),
  *     >0 = argument error;
- *   - one process drives one GPU from one thread at a time (the reference is single-threaded): the
- *     smoother kernels share a device-side ticket counter and error flag, so two smoother calls must
- *     not run concurrently on different streams of the same process;
+ *   - one host thread drives a GPU at a time (the reference is single-threaded): the smoother kernels
+ *     share one device-side ticket counter and error flag PER DEVICE (allocated on first use on the
+ *     current device), so two smoother calls must not run concurrently on different streams of the
+ *     same device; one process may drive several devices (cudaSetDevice before each call);
  *   - all reals are IEEE fp64, all indices int32 (scipy's default index type, which the
  *     reference's sp.bsr_array uses);
  *   - BSR layout is scipy's: data[nnzb][b][b] row-major blocks, indices[nnzb] ascending
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DGB_ABI_VERSION 4
+#define DGB_ABI_VERSION 5
 
 /* ---- status ------------------------------------------------------------------------- */
 int dgb_abi_version(void);
@@ -55,7 +56,9 @@ typedef struct dgb_smoother_ctl {
     double res0;      /* RMS residual at smoother entry            (relaxation.py:202) */
     double ratio;     /* last normalised residual                  (relaxation.py:208) */
     int32_t skip;     /* ratio < 1e-6 seen -> stop sweeping        (relaxation.py:211-213) */
-    int32_t diverged; /* ratio > 1e10 seen -> caller raises/exits  (relaxation.py:214-216) */
+    int32_t diverged; /* ratio > 1e10 seen -> caller raises/exits  (relaxation.py:214-216); STICKY: only the
+                         host clears it, and while it is set every later smoother call on this block is
+                         skipped (the reference has left the process at this point) */
     int32_t iters;    /* completed iterations of this call */
     int32_t calls;    /* smoother calls since the block was zeroed */
 } dgb_smoother_ctl;
@@ -96,14 +99,19 @@ typedef struct dgb_operator {
 #define DGB_FLAG_GHOST_HI 16
 
 /* 0 = auto (single-launch smoother kernels where the operator allows), 1 = generic kernels only.
- * Tuning values (tests and probes): 100+v experiment switch of the smoother kernels, 200+b smallest block
- * size for the TMA-staged apply kernel (off by default), 300+mask block sizes the chained Gauss-Seidel kernel is
- * used for (bit 0..4 = b 4, 9, 16, 25, 36; default all), 400+n CTAs per thread-block cluster of that kernel.
+ * Tuning values (tests and probes): 100+v experiment switch of the smoother kernels, 300+mask block sizes the
+ * chained Gauss-Seidel kernel is used for (bit 0..4 = b 4, 9, 16, 25, 36; default all), 400+n CTAs per
+ * thread-block cluster of that kernel.
  * Returns the previous setting of the 0/1 switch. */
 int dgb_set_kernel_path(int32_t path);
-/* Error flag of the asynchronous kernels (0 ok, 1 = TMA/mbarrier wait timed out, 2 = row
- * dependency wait timed out).  Synchronises the device. */
+/* Error flag of the asynchronous kernels of the current device (0 ok, 1 = TMA/mbarrier wait timed out,
+ * 2 = row dependency wait timed out).  Synchronises the device.  A non-zero flag means the pass that raised it
+ * (and every later one until the flag is reset) returned early: u is partly updated and the level's
+ * gs_mailbox may hold stale values -- reset the flag, refill every gs_mailbox with dgb_fill_sentinel and treat
+ * the solve as failed. */
 int dgb_device_error(int32_t reset);
+/* v[0..n) = all-ones NaN (the "not delivered" mark of gs_mailbox). */
+int dgb_fill_sentinel(double *v, int64_t n, void *stream);
 
 /* ---- K5: block-sparse operator apply / residual ---------------------------------------
  * replaces  grid.BSR @ u  (scipy bsr_matvec) -- dgfem/solver.py:117,119,150;
@@ -195,7 +203,7 @@ int dgb_block_relax_sweep(const dgb_operator *h_op, const double *rhs, const dou
                           double *x_out, double omega, void *stream);
 
 /* ---- smoother control ------------------------------------------------------------------ */
-/* ctl->res0 = sqrt(*sumsq / n); skip = diverged = iters = 0; calls += 1 */
+/* ctl->res0 = sqrt(*sumsq / n); skip = diverged (sticky); iters = 0; calls += 1 */
 int dgb_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream);
 /* ratio = sqrt(*sumsq / n) / res0; apply the 1e-6 / 1e10 tests; iters += 1 (unless skipped) */
 int dgb_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, int64_t n, void *stream);
@@ -253,11 +261,16 @@ typedef struct dgb_level {
     int32_t pad0;
     const double *R;
     const double *P;
-    /* smoother settings of the coarsening that owns this level (paramfile.yml:20-65) */
+    /* smoother settings of the coarsening that owns this level (paramfile.yml:20-65): the pre-smoother
+     * (also the coarsest level's 'smoother' solver, dgfem/solver.py:202-204) ... */
     int32_t smoother;        /* DGB_SMOOTHER_*                                 */
     int32_t direction;       /* 0 symmetric, +1 forward, -1 backward           */
     int32_t pre_iterations, post_iterations;
     double omega;
+    /* ... and the post-smoother, resolved independently (dgfem/solver.py:144,196) */
+    int32_t post_smoother;   /* DGB_SMOOTHER_*                                 */
+    int32_t post_direction;
+    double post_omega;
 } dgb_level;
 
 #define DGB_SMOOTHER_BLOCK_GS_PYAMG 0
@@ -268,12 +281,26 @@ typedef struct dgb_vcycle_opts {
     int32_t gs_mode;            /* DGB_GS_LEXICOGRAPHIC | DGB_GS_REDBLACK       */
     int32_t check_residual;     /* 1 = reference semantics (early exit active)  */
     int32_t coarse_iterations;  /* 10 in the reference (solver.py:204)          */
-    int32_t reserved;
+    int32_t coarse_solver;      /* DGB_COARSE_SMOOTHER | DGB_COARSE_DIRECT      */
     void *u_final_event;        /* optional cudaEvent_t, recorded on `stream` right after the last kernel
                                    that writes the finest level's u (the post-smoother's closing residual
                                    test only reads it): a caller may copy u out on another stream from
                                    there on.  NULL = not used.                  */
+    const double *coarse_inverse; /* DGB_COARSE_DIRECT: dense inverse [n x n] of levels[0]'s operator,
+                                   n = Ni*Nj*b (dgb_dense_inverse)              */
 } dgb_vcycle_opts;
+
+/* coarse grid solver (paramfile.yml:23, dgfem/solver.py:199-204) */
+#define DGB_COARSE_SMOOTHER 0
+#define DGB_COARSE_DIRECT 1
+
+/* Coarse-grid direct solve, replaces  splin.spsolve(grid.BSR.tocsr(), RHS)  (dgfem/solver.py:56-59,199-200):
+ * dgb_dense_inverse expands the BSR operator of a (small) level into a dense n x n matrix, n = n_brow*b, and
+ * inverts it in place by Gauss-Jordan elimination with partial pivoting (once per hierarchy); *info (device
+ * int) = 1 + column of the first zero pivot.  dgb_dense_solve then is u = inverse * rhs. */
+int dgb_dense_inverse(const double *data, const int32_t *indices, const int32_t *indptr, int32_t n_brow,
+                      int32_t b, double *inverse, int32_t *info, void *stream);
+int dgb_dense_solve(const double *inverse, int32_t n, const double *rhs, double *u, void *stream);
 
 /* One V-cycle on the finest level: levels[n-1].u is updated in place from levels[n-1].rhs.
  * ctl: array of nlevels control blocks (device); partials/sumsq: workspaces. */

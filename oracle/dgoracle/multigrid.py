@@ -96,25 +96,58 @@ class Hierarchy:
 
 
 class Schedule:
-    """The smoother settings of paramfile.yml:20-65 (defaults = shipped values)."""
+    """The smoother settings of paramfile.yml:20-65 (defaults = shipped values).  The post smoother is
+    resolved independently of the pre smoother (dgfem/solver.py:143-147,196): post_smoother / post_direction /
+    post_omega default to the pre smoother's values.
+    gs_mode: 'lexicographic' (the reference), 'redblack', or 'slab_lexicographic' with `world` slabs -- the
+    product's multi-GPU variants (dg_multigrid_solver_b200/parallel.py); levels with fewer than `min_rows`
+    element rows per slab are gathered to one GPU and use the lexicographic order."""
 
     def __init__(self, smoother="block_gauss_seidel_pyamg", direction="symmetric", pre=2, post=1,
-                 coarse_iterations=10, omega=1.0, coarse_solver="smoother", gs_mode="lexicographic"):
+                 coarse_iterations=10, omega=1.0, coarse_solver="smoother", gs_mode="lexicographic",
+                 post_smoother=None, post_direction=None, post_omega=None, world=1, min_rows=8):
         self.smoother, self.direction, self.pre, self.post = smoother, direction, pre, post
         self.coarse_iterations, self.omega, self.coarse_solver = coarse_iterations, omega, coarse_solver
         self.gs_mode = gs_mode
+        self.post_smoother = smoother if post_smoother is None else post_smoother
+        self.post_direction = direction if post_direction is None else post_direction
+        self.post_omega = omega if post_omega is None else post_omega
+        self.world, self.min_rows = world, min_rows
 
 
-def _smooth(level, sched, RHS, u, iterations):
-    if sched.smoother == "block_gauss_seidel_pyamg":
+def slabs_of_level(H, k, sched):
+    """Number of slabs level index k (0 = coarsest) is smoothed in under `sched` (1 = gathered / one GPU):
+    restates parallel.distributed_levels -- p-levels are always distributed; an h-level (coarsening factor
+    cf) is distributed iff Nj % (world*cf) == 0, it keeps >= min_rows rows per rank, and every finer h-level
+    is distributed too."""
+    if sched.gs_mode != "slab_lexicographic" or sched.world <= 1:
+        return 1
+    Nj = H.levels[-1].Nj
+    lev = H.levels[k]
+    if lev.cf is None:
+        return sched.world
+    for cf in sorted(L.cf for L in H.levels if L.cf is not None):
+        ok = Nj % (sched.world * cf) == 0 and Nj // sched.world // cf >= sched.min_rows
+        if not ok:
+            return 1
+        if cf == lev.cf:
+            return sched.world
+    return 1
+
+
+def _smooth(level, sched, RHS, u, iterations, post=False, slabs=1):
+    smoother = sched.post_smoother if post else sched.smoother
+    direction = sched.post_direction if post else sched.direction
+    omega = sched.post_omega if post else sched.omega
+    if smoother == "block_gauss_seidel_pyamg":
         if sched.gs_mode == "redblack":
-            return relax.red_black_gauss_seidel(level.A, RHS, level.Ni, level.Nj, u, sched.direction, iterations)
-        return relax.block_gauss_seidel_pyamg(level.A, RHS, u, sched.direction, sched.omega, iterations)
-    if sched.smoother == "block_jacobi":
-        return relax.block_jacobi(level.A, RHS, u, sched.direction, sched.omega, iterations)
-    if sched.smoother == "block_gauss_seidel":
-        return relax.block_gauss_seidel(level.A, RHS, u, sched.direction, sched.omega, iterations)
-    raise AttributeError(sched.smoother)
+            return relax.red_black_gauss_seidel(level.A, RHS, level.Ni, level.Nj, u, direction, iterations)
+        return relax.block_gauss_seidel_pyamg(level.A, RHS, u, direction, omega, iterations, slabs=slabs)
+    if smoother == "block_jacobi":
+        return relax.block_jacobi(level.A, RHS, u, direction, omega, iterations)
+    if smoother == "block_gauss_seidel":
+        return relax.block_gauss_seidel(level.A, RHS, u, direction, omega, iterations)
+    raise AttributeError(smoother)
 
 
 def restrict(H, k, residual):
@@ -140,19 +173,20 @@ def prolong(H, k, u_coarse):
 def v_cycle(H, sched, k, RHS, u):
     """solver.py:141-207."""
     lev = H.levels[k - 1]
+    slabs = slabs_of_level(H, k - 1, sched)
     if k > 1:
-        u = _smooth(lev, sched, RHS, u, sched.pre)
+        u = _smooth(lev, sched, RHS, u, sched.pre, slabs=slabs)
         residual = RHS - lev.A @ u
         RHS_c = restrict(H, k, residual)
         u_c = v_cycle(H, sched, k - 1, RHS_c, np.zeros_like(RHS_c))
         u = u + prolong(H, k, u_c)                 # the reference does u += ... on the smoother's fresh copy
-        u = _smooth(lev, sched, RHS, u, sched.post)
+        u = _smooth(lev, sched, RHS, u, sched.post, post=True, slabs=slabs)
     else:
         if sched.coarse_solver == "direct":
             import scipy.sparse.linalg as splin
             u = splin.spsolve(lev.A.to_scipy().tocsr(), RHS)
         else:
-            u = _smooth(lev, sched, RHS, u, sched.coarse_iterations)
+            u = _smooth(lev, sched, RHS, u, sched.coarse_iterations, slabs=slabs)
     return u
 
 

@@ -73,15 +73,44 @@ def gs_pass(A, x, b, direction):
         raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
 
 
+def slab_gs_pass(A, x, b, direction, slabs):
+    """One directional pass of the product's `slab_lexicographic` multi-GPU mode (NOT the reference's
+    iteration): the block rows are split into `slabs` contiguous, equally sized slabs (one per GPU); every
+    slab runs pyamg's lexicographic pass over its own rows, reading the rows of the other slabs as they were
+    BEFORE the pass (the halo exchanged ahead of the pass) -- block-Jacobi coupling between slabs."""
+    if direction == "symmetric":
+        slab_gs_pass(A, x, b, "forward", slabs)
+        slab_gs_pass(A, x, b, "backward", slabs)
+        return
+    if direction not in ("forward", "backward"):
+        raise ValueError('valid sweep directions: "forward", "backward", and "symmetric"')
+    assert A.N % slabs == 0
+    rows = A.N // slabs
+    Dinv = A.dinv()
+    frozen = x.copy()
+    for s in range(slabs):
+        xs = frozen.copy()
+        r0, r1 = s * rows, (s + 1) * rows
+        if direction == "forward":
+            native.block_gauss_seidel(A.indptr, A.indices, A.data, xs, b, Dinv, r0, r1, 1, A.b)
+        else:
+            native.block_gauss_seidel(A.indptr, A.indices, A.data, xs, b, Dinv, r1 - 1, r0 - 1, -1, A.b)
+        x[r0 * A.b:r1 * A.b] = xs[r0 * A.b:r1 * A.b]
+
+
 def block_gauss_seidel_pyamg(A, RHS, u=None, direction="symmetric", omega=1, max_iterations=1000,
-                             info=None):
-    """relaxation.py:198-218 (omega is accepted and ignored, as in the reference)."""
+                             info=None, slabs=1):
+    """relaxation.py:198-218 (omega is accepted and ignored, as in the reference).  slabs > 1: the
+    product's slab_lexicographic variant (slab_gs_pass), same residual tests."""
     u = np.zeros_like(RHS) if not isinstance(u, np.ndarray) else u.copy()
     residual_0 = lp_norm(RHS - A @ u, 2)
     n = 0
     with np.errstate(divide="ignore", invalid="ignore"):
         while n < max_iterations:
-            gs_pass(A, u, RHS, direction)
+            if slabs > 1:
+                slab_gs_pass(A, u, RHS, direction, slabs)
+            else:
+                gs_pass(A, u, RHS, direction)
             residual = lp_norm(RHS - A @ u, 2) / residual_0
             if residual < 1e-6:
                 if info is not None:

@@ -27,8 +27,10 @@ REF = "/root/reference"
 GOLD = os.path.join(REPO, "tests", "golden")
 
 
-def _mg(levels_u, factors, smoother="block_gauss_seidel_pyamg", coarse="smoother"):
-    return {"levels_u": levels_u, "factors": factors, "smoother": smoother, "coarse": coarse}
+def _mg(levels_u, factors, smoother="block_gauss_seidel_pyamg", coarse="smoother", post=None):
+    """post: optional overrides of every coarsening's post smoother (smoother / direction / iterations /
+    relaxation factor) -- the reference resolves pre and post independently (dgfem/solver.py:143-147,196)."""
+    return {"levels_u": levels_u, "factors": factors, "smoother": smoother, "coarse": coarse, "post": post}
 
 
 # name -> dict(grid file, P_grid, p_u, O-grid, circular, sigma multiplier, mode, multigrid settings)
@@ -47,6 +49,14 @@ CASES = {
                       mode="multigrid", mg=_mg("2,1", "2,4"), dump="full"),
     "circ8_h24": dict(grid="CircleInCircle_8X8_nPoly2.xyz", pg=2, pu=2, ogrid=True, circ=True, sigmul=2.0,
                       mode="multigrid", mg=_mg("2,1", "2,4"), dump="full"),
+    # coarse grid solver: direct (dgfem/solver.py:56-59,199-200) on the same hierarchy
+    "rect8_direct": dict(grid="Rectangle_8X8_nPoly2.xyz", pg=2, pu=2, ogrid=False, circ=False, sigmul=1.0,
+                         mode="multigrid", mg=_mg("2,1", "2,4", coarse="direct"), dump="light"),
+    # pre smoother != post smoother (different plugin, direction, iteration count and relaxation factor)
+    "rect8_prepost": dict(grid="Rectangle_8X8_nPoly2.xyz", pg=2, pu=2, ogrid=False, circ=False, sigmul=1.0,
+                          mode="multigrid",
+                          mg=_mg("2,1", "2", post={"smoother": "block_gauss_seidel", "direction": "forward",
+                                                   "iterations": 2, "relaxation factor": 0.9}), dump="light"),
     # p=1 geometry
     "rect4_p1": dict(grid="Rectangle_4X4_nPoly1.xyz", pg=1, pu=1, ogrid=False, circ=False, sigmul=1.0,
                      mode="multigrid", mg=_mg("1", 2), dump="full"),
@@ -142,6 +152,8 @@ def worker(name):
         for blk in (pc, gc):
             for s in ("pre smoother", "post smoother"):
                 blk[s]["smoother"] = mg["smoother"]
+            if mg.get("post"):
+                blk["post smoother"].update(mg["post"])
         params["solver"]["multigrid"]["coarse grid solver"] = mg["coarse"]
         s = Settings(params)
         d = DGFEM(settings=s, solve_multigrid=True)
@@ -179,6 +191,25 @@ def worker(name):
         out["coarse_bgs_10"] = Relaxation.block_gauss_seidel_pyamg(
             grid=g0, RHS=rhs0, u=np.zeros_like(rhs0), direction="symmetric", max_iterations=10, omega=1.0)
         out["A_u0_fine"] = fine.BSR @ u0
+        # pyamg-free pin of the BACKWARD pass: the reference's own NumPy block_gauss_seidel (forward,
+        # dgfem/relaxation.py:170-195) on the block-reversed system P A P^T equals a backward pass on A
+        import types
+        import scipy.sparse as sp
+        B = fine.BSR
+        b = B.blocksize[0]
+        N = B.shape[0] // b
+        perm = (np.arange(N)[::-1, None] * b + np.arange(b)[None, :]).ravel()      # block order reversed
+        Arev = sp.bsr_array(sp.csr_array(B.tocsr())[perm][:, perm], blocksize=(b, b))
+        Arev.sort_indices()
+        stand_in = types.SimpleNamespace(BSR=Arev, BSR_D=None, BSR_E=None, BSR_F=None)
+        ub = Relaxation.block_gauss_seidel(stand_in, fine.RHS[perm], u=u0[perm], max_iterations=1, omega=1)
+        out["bgs_numpy_backward_1"] = ub[perm]
+        fine.BSR_E = fine.BSR_D = fine.BSR_F = None
+        uf = Relaxation.block_gauss_seidel(fine, fine.RHS, u=u0, max_iterations=1, omega=1)
+        out["bgs_numpy_forward_1"] = uf
+        stand_in = types.SimpleNamespace(BSR=Arev, BSR_D=None, BSR_E=None, BSR_F=None)
+        out["bgs_numpy_symmetric_1"] = Relaxation.block_gauss_seidel(stand_in, fine.RHS[perm], u=uf[perm],
+                                                                     max_iterations=1, omega=1)[perm]
     elif case["mode"] == "smoother":
         from dgfem.relaxation import Relaxation
         s = Settings(params)

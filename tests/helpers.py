@@ -39,9 +39,36 @@ def case_params(case, gs_mode="lexicographic", check_residual=True):
     p["solver"]["b200"]["check residual"] = check_residual
     mg = case.get("mg")
     if mg:
-        p["solver"]["multigrid"]["polynomial coarsening"]["levels"]["u"] = mg["levels_u"]
-        p["solver"]["multigrid"]["geometric coarsening"]["coarsening factors"] = mg["factors"]
+        pc = p["solver"]["multigrid"]["polynomial coarsening"]
+        gc = p["solver"]["multigrid"]["geometric coarsening"]
+        pc["levels"]["u"] = mg["levels_u"]
+        gc["coarsening factors"] = mg["factors"]
+        for blk in (pc, gc):                       # the same edits oracle/gen_golden.py applied to the reference
+            if mg.get("smoother"):
+                for s in ("pre smoother", "post smoother"):
+                    blk[s]["smoother"] = mg["smoother"]
+            if mg.get("post"):
+                blk["post smoother"].update(mg["post"])
+        if mg.get("coarse"):
+            p["solver"]["multigrid"]["coarse grid solver"] = mg["coarse"]
     return p
+
+
+def oracle_schedule(case, **kw):
+    """dgoracle.multigrid.Schedule of a fixture case (coarse solver, independent post smoother)."""
+    from dgoracle import multigrid
+    mg = case.get("mg") or {}
+    post = mg.get("post") or {}
+    args = dict(coarse_solver=mg.get("coarse", "smoother"))
+    if mg.get("smoother"):
+        args["smoother"] = mg["smoother"]
+    if post:
+        args.update(post_smoother=post.get("smoother"), post_direction=post.get("direction"),
+                    post_omega=post.get("relaxation factor"))
+        if "iterations" in post:
+            args["post"] = post["iterations"]
+    args.update(kw)
+    return multigrid.Schedule(**args)
 
 
 def make_settings(case, **kw):

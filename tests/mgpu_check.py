@@ -2,7 +2,9 @@
 """Multi-GPU parity check, launched with torchrun (one rank per GPU):
   red-black across slabs      == single-GPU red-black          (same iteration; norms reduced in another order)
   exact lexicographic pipeline == single-GPU lexicographic      (the reference's sweep order)
-  slab-lexicographic           converges (hybrid, not the reference's iteration)
+  slab-lexicographic           == the oracle's restatement of that iteration (dgoracle.relax.slab_gs_pass:
+                                  lexicographic inside a slab, halo frozen at the previous pass), same cycle count
+Histories are compared at rtol 1e-10 + atol 1e-12 (the single-GPU tolerance, tests/test_gpu_parity.py).
 usage: torchrun --nproc-per-node N tests/mgpu_check.py [N_elements]"""
 import os
 import sys
@@ -47,15 +49,18 @@ def main():
             ref = np.array(d.solver.residuals)
         if rank == 0:
             msg = f"[mgpu_check] world={world} n={n} mode={mode}: {len(hist) - 1} cycles, final {hist[-1]:.3e}"
+        if rank == 0 and single_mode is None:
+            # the oracle's slab iteration on the same grid (CPU; the reference's assembly restated in NumPy)
+            from dgoracle import multigrid, plot3d
+            x, y = plot3d.rectangle_nodes(n, n, 2)
+            H = multigrid.Hierarchy(x, y, 2, [2, 1], bench.h_factors(n))
+            _, ref = multigrid.solve_multigrid(H, multigrid.Schedule(gs_mode="slab_lexicographic", world=world, min_rows=8))
+        if rank == 0:
             if ref is not None:
-                same = len(ref) == len(hist) and np.allclose(hist, ref, rtol=1e-8, atol=1e-12)
-                msg += f" | single-GPU {len(ref) - 1} cycles, max rel diff " \
+                same = len(ref) == len(hist) and np.allclose(hist, ref, rtol=1e-10, atol=1e-12)
+                msg += f" | {'single-GPU' if single_mode else 'oracle'} {len(ref) - 1} cycles, max rel diff " \
                        f"{np.max(np.abs(hist[:len(ref)] - ref[:len(hist)]) / ref[:len(hist)]):.2e} -> {'OK' if same else 'MISMATCH'}"
                 ok &= bool(same)
-            else:
-                conv = hist[-1] < 1e-6
-                msg += f" -> {'OK (converged)' if conv else 'NOT CONVERGED'}"
-                ok &= bool(conv)
             print(msg, flush=True)
         del ds
         torch.cuda.empty_cache()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(lib)
     for name in _declared_symbols():
         assert hasattr(L, name), f"{name} declared in include/dgb200.h but not exported"
-    assert L.dgb_abi_version() == 4
+    assert L.dgb_abi_version() == 5
     assert L.dgb_partials_len() >= 1024
 
 
@@ -38,6 +38,25 @@ def test_ctypes_binding_covers_the_header():
     assert set(_lib.SIGNATURES) == set(_declared_symbols())
     assert ctypes.sizeof(_lib.SmootherCtl) == 32
     _lib.load()
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the ABI, C compiler vs ctypes."""
+    import subprocess
+    from dg_multigrid_solver_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dgb200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(dgb_operator), sizeof(dgb_level),'
+                   ' sizeof(dgb_vcycle_opts), sizeof(dgb_smoother_ctl), sizeof(dgb_tables_desc),'
+                   ' offsetof(dgb_level, post_omega), offsetof(dgb_vcycle_opts, coarse_inverse),'
+                   ' offsetof(dgb_level, R));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.Operator), ctypes.sizeof(_lib.Level), ctypes.sizeof(_lib.VcycleOpts),
+            ctypes.sizeof(_lib.SmootherCtl), ctypes.sizeof(_lib.TablesDesc), _lib.Level.post_omega.offset,
+            _lib.VcycleOpts.coarse_inverse.offset, _lib.Level.R.offset]
+    assert got == want
 
 
 def test_product_has_no_cpu_path():

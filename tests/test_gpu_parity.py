@@ -9,7 +9,7 @@ from helpers import CASES, golden, grid_path, make_settings, oracle_hierarchy, r
 
 pytestmark = pytest.mark.gpu
 
-MG_CASES = ["c1", "rect4_p1", "rect8_h24", "circ8_h24", "c2", "shipped"]
+MG_CASES = ["c1", "rect4_p1", "rect8_h24", "circ8_h24", "c2", "shipped", "rect8_direct", "rect8_prepost"]
 HIST_RTOL, HIST_ATOL = 1e-10, 1e-12      # see tests/test_oracle_vs_golden.py
 
 
@@ -57,6 +57,7 @@ def test_apply_and_smoother_calls(mg):
         u = Relaxation.block_gauss_seidel_pyamg(grid=fine, RHS=fine.RHS, u=u0, direction=direction,
                                                 max_iterations=1, omega=1.0)
         assert rel_err(u, g[f"bgs_pyamg_{direction}_1"]) < 1e-12
+        assert rel_err(u, g[f"bgs_numpy_{direction}_1"]) < 1e-12        # pyamg-free pin (reference NumPy sweep)
         assert np.array_equal(u0, g["smooth_u0"])                      # inputs are never mutated
     u = Relaxation.block_gauss_seidel_pyamg(grid=fine, RHS=fine.RHS, u=u0, direction="symmetric", max_iterations=2)
     assert rel_err(u, g["bgs_pyamg_symmetric_2"]) < 1e-12
@@ -106,8 +107,8 @@ def test_smoother_only_runs(name):
 
 @pytest.mark.parametrize("name", ["c1", "c2", "circ8_h24", "shipped"])
 def test_streaming_kernels_match_generic_kernels(name):
-    """Every level of the hierarchy (b = 4, 9, 16, 36; Dirichlet and O-grid stencils): the TMA-streaming
-    kernels (k_stream, k_gs_rows) against the generic row-per-thread kernels, call by call."""
+    """Every level of the hierarchy (b = 4, 9, 16, 36; Dirichlet and O-grid stencils): the single-launch
+    lexicographic kernels (k_gs_chain, k_gs_rows) against the generic per-anti-diagonal kernels, call by call."""
     import torch
     from dg_multigrid_solver_b200 import _lib
     from dg_multigrid_solver_b200.relaxation import Relaxation, bsr_apply, residual_norm
@@ -115,7 +116,6 @@ def test_streaming_kernels_match_generic_kernels(name):
     L = _lib.load()
     rng = np.random.default_rng(11)
     try:
-        L.dgb_set_kernel_path(200 + 1)          # k_stream for every block size (default: b >= 16 only)
         for grid in d.grids:
             assert grid.stencil >= 0 and grid.d_gs is not None
             n = grid.d_rhs.numel()

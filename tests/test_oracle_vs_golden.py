@@ -3,9 +3,9 @@ reference's own code (oracle/gen_golden.py -> tests/golden/*.npz)."""
 import numpy as np
 import pytest
 
-from helpers import CASES, golden, oracle_hierarchy, rel_err
+from helpers import CASES, golden, oracle_hierarchy, oracle_schedule, rel_err
 
-MG_CASES = ["c1", "rect4_p1", "rect8_h24", "circ8_h24", "c2", "shipped"]
+MG_CASES = ["c1", "rect4_p1", "rect8_h24", "circ8_h24", "c2", "shipped", "rect8_direct", "rect8_prepost"]
 # residual histories are normalised by the initial residual; entries near the 1e-7 floor carry the
 # rounding noise of evaluating RHS - A u (~1e-16 * |RHS| / |r|), so the 1e-10 bar of BASELINE.json
 # is relative to the initial residual (= absolute on the normalised history) with rtol on top
@@ -80,10 +80,26 @@ def test_apply_and_single_sweeps(mg):
     assert rel_err(u, g["coarse_bgs_10"]) < 1e-12
 
 
+def test_backward_and_symmetric_pass_pinned_without_pyamg(mg):
+    """pyamg's C++ sweep is restated (it is not installable offline).  Its forward pass is pinned by the
+    reference's own NumPy block_gauss_seidel (dgfem/relaxation.py:170-195); the BACKWARD pass by the same
+    NumPy code run on the block-reversed system P A P^T (oracle/gen_golden.py), which is a backward pass on A;
+    symmetric = forward then backward.  Both the golden (restated pyamg under the reference's wrapper) and
+    the oracle's C sweep must agree with those pyamg-free vectors."""
+    from dgoracle import relax
+    name, g, H = mg
+    fine = H.levels[-1]
+    u0 = g["smooth_u0"]
+    for d in ("forward", "backward", "symmetric"):
+        assert rel_err(g[f"bgs_pyamg_{d}_1"], g[f"bgs_numpy_{d}_1"]) < 1e-12
+        u = relax.block_gauss_seidel_pyamg(fine.A, fine.RHS, u0, d, 1, 1)
+        assert rel_err(u, g[f"bgs_numpy_{d}_1"]) < 1e-12
+
+
 def test_vcycle_and_history(mg):
     from dgoracle import multigrid
     name, g, H = mg
-    s = multigrid.Schedule()
+    s = oracle_schedule(CASES[name])
     fine = H.levels[-1]
     u1 = multigrid.v_cycle(H, s, len(H.levels), fine.RHS, np.zeros_like(fine.RHS))
     assert rel_err(u1, g["u_after_1_vcycle"]) < 1e-11
@@ -121,6 +137,36 @@ def test_c1_matches_survey_appendix_c():
     assert list(g["L2_indices"][:10]) == [0, 1, 4, 0, 1, 2, 5, 1, 2, 3]
     assert np.allclose(g["L2_data"][0][0, :3], [144, 6.928203230275689, 80.49844718999263], rtol=1e-13)
     assert abs(float(g["L2_error"]) - 6.951699e-02) < 1e-7
+
+
+def test_new_cases_exercise_what_they_claim():
+    g, h = golden("rect8_direct"), golden("rect8_h24")
+    assert len(g["residuals"]) == len(h["residuals"]) and not np.allclose(g["residuals"], h["residuals"], rtol=HIST_RTOL, atol=0)
+    assert CASES["rect8_direct"]["mg"]["coarse"] == "direct"
+    assert CASES["rect8_prepost"]["mg"]["post"]["smoother"] == "block_gauss_seidel"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_lexicographic_oracle(world):
+    """The product's multi-GPU iteration (lexicographic inside a slab, halo frozen at the previous pass):
+    one slab reproduces the lexicographic sweep bit for bit; G slabs converge in a similar cycle count."""
+    from dgoracle import multigrid, relax
+    H = oracle_hierarchy(CASES["rect8_h24"])
+    fine = H.levels[-1]
+    u0 = np.sin(0.37 * np.arange(fine.RHS.size)) * 0.1
+    a = relax.block_gauss_seidel_pyamg(fine.A, fine.RHS, u0, "symmetric", 1, 2)
+    b = relax.block_gauss_seidel_pyamg(fine.A, fine.RHS, u0, "symmetric", 1, 2, slabs=1)
+    assert np.array_equal(a, b)
+    x1, x2 = u0.copy(), u0.copy()
+    relax.slab_gs_pass(fine.A, x1, fine.RHS, "forward", world)
+    relax.gs_pass(fine.A, x2, fine.RHS, "forward")
+    rows = fine.A.N // world * fine.b
+    assert np.array_equal(x1[:rows], x2[:rows]) and not np.array_equal(x1[rows:], x2[rows:])   # first slab unaffected
+    s = multigrid.Schedule(gs_mode="slab_lexicographic", world=world, min_rows=2)
+    assert [multigrid.slabs_of_level(H, k, s) for k in range(4)] == ([1, world, world, world] if world == 2 else [1, 1, 4, 4])
+    _, hist = multigrid.solve_multigrid(H, s)
+    _, ref = multigrid.solve_multigrid(H, multigrid.Schedule())
+    assert hist[-1] < 1e-6 and len(hist) <= len(ref) + 2
 
 
 def test_redblack_oracle_converges():
