@@ -10,13 +10,21 @@ A "step" is one multigrid V-cycle on the finest level (Solver.multigrid_V_cycle)
   value      V-cycles/s, device-timed (CUDA events), operator + vectors resident in HBM
   e2e        the same cycle through Solver.multigrid_V_cycle with HOST (pinned) RHS/u in and u out:
              host->device and device->host copies inside the timed region
-  roofline   the dominant kernel family (one directional block-GS pass over the fine level), with
-             algorithmic bytes from SURVEY.md section 8d
+  roofline   the kernel with the largest measured share of the V-cycle (launches per cycle x CUDA-event time per
+             launch, counted from the schedule the library runs), algorithmic bytes per launch as DESIGN.md
+             section 4 states them, DRAM traffic from the tracked ncu summaries (profiles/r02_ncu_traffic.json)
+  vcycle     bytes_min of SURVEY.md section 8d (6 passes + 1 residual per level) AND the bytes the library's
+             kernels must move, each over the measured time -- never the reference schedule's 12 passes/level
   cpu_baseline  the oracle (CPU restatement of the reference: scipy-order BSR matvec + restated
-             pyamg block-GS in C, single thread like the reference) on a bounded sample
+             pyamg block-GS in C, single thread like the reference) on a bounded sample: one V-cycle of the
+             same level structure on a --cpu-sample^2 grid.  `measured` is the un-scaled rate on that grid,
+             `value` the same rate scaled by DOFs to the full grid (the per-DOF cost of a V-cycle is flat in n)
+  parity     the GPU V-cycle on the CPU sample grid against the oracle's (same inputs), inside the bench
 
---impl reference times that CPU restatement alone (the reference is pure Python + pyamg/scipy
-native code; it cannot run the 2048^2 case).
+--config c4 / c5 run BASELINE.json configs[3] / configs[4] at full size (p=5 apply / block-Jacobi / block-GS
+sweeps + assembly; Stokes assembly + apply) and print one line each in the same contract.
+--impl reference times the CPU restatement alone (the reference is pure Python + pyamg/scipy native code; it
+cannot run the 2048^2 case): a step = one oracle V-cycle on the sample grid.
 """
 import argparse
 import json
@@ -127,7 +135,7 @@ def measured_peak():
 
 def cpu_reference_vcycle(n_sample, p, steps, warmup):
     """Oracle V-cycle on an n_sample^2 grid with the same level structure; returns (seconds per
-    V-cycle, sample DOFs, setup seconds)."""
+    V-cycle, sample DOFs, setup seconds, u after the first V-cycle from u = 0)."""
     from dgoracle import multigrid, plot3d
     t0 = time.perf_counter()
     x, y = plot3d.rectangle_nodes(n_sample, n_sample, p)
@@ -137,32 +145,50 @@ def cpu_reference_vcycle(n_sample, p, steps, warmup):
     fine = H.levels[-1]
     sched = multigrid.Schedule()
     u = np.zeros_like(fine.RHS)
-    for _ in range(warmup):
+    u_first = None
+    for _ in range(max(warmup, 1)):
         u = multigrid.v_cycle(H, sched, len(H.levels), fine.RHS, u)
+        if u_first is None:
+            u_first = u.copy()
     t0 = time.perf_counter()
     for _ in range(steps):
         u = multigrid.v_cycle(H, sched, len(H.levels), fine.RHS, u)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dt, fine.RHS.size, setup
+    return dt, fine.RHS.size, setup, u_first
 
 
 def run_reference(args):
+    """--impl reference: the CPU arm alone.  A step = one oracle V-cycle on the sample grid (same level structure as
+    the workload); ms_per_step is what was measured, `value` the DOF-scaled full-grid equivalent (stated in
+    cpu_baseline.sample / measured)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, p = args.size, args.p
     full_dofs = n * n * (p + 1) ** 2
-    dt, sample_dofs, setup = cpu_reference_vcycle(args.cpu_sample, p, args.steps, min(args.warmup, 1))
+    dt, sample_dofs, setup, _ = cpu_reference_vcycle(args.cpu_sample, p, args.steps, min(args.warmup, 1))
     value = (1.0 / dt) * (sample_dofs / full_dofs)
-    sample = (f"oracle V-cycle on Rectangle {args.cpu_sample}x{args.cpu_sample} p={p} (same level structure), "
-              f"{sample_dofs} DOFs, scaled by DOFs to {n}x{n}; setup {setup:.1f}s not timed")
+    cpu = cpu_baseline_block(args, dt, sample_dofs, setup, full_dofs)
+    cfg = workload_config(args)
+    cfg["cpu_sample"] = f"Rectangle {args.cpu_sample}x{args.cpu_sample} (timed), DOF-scaled to {n}x{n} (value)"
     line = {"impl": "reference", "metric": "multigrid_vcycles_per_s", "value": value, "unit": "V-cycles/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "ms_per_step_is": "one oracle V-cycle on the sample grid (un-scaled)",
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "V-cycles/s", "cores": 1, "kind": "port", "sample": sample},
+            "config": cfg, "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_block(args, dt, sample_dofs, setup, full_dofs):
+    n, p, m = args.size, args.p, args.cpu_sample
+    return {"value": (1.0 / dt) * (sample_dofs / full_dofs), "unit": "V-cycles/s", "cores": 1, "kind": "port",
+            "measured": {"grid": f"{m}x{m}", "dofs": sample_dofs, "s_per_vcycle": dt, "vcycles_per_s": 1.0 / dt,
+                         "dof_per_s": sample_dofs / dt, "setup_s_not_timed": setup},
+            "sample": f"oracle (C/NumPy restatement of the reference, single thread like the reference's scipy/pyamg "
+                      f"path) V-cycle on Rectangle {m}x{m} p={p}, same level structure: {dt:.3f} s per cycle "
+                      f"measured; `value` scales that by DOFs ({sample_dofs} -> {full_dofs}) to {n}x{n}, which the "
+                      f"CPU path cannot assemble in bench time; host has {os.cpu_count()} cores"}
 
 
 def workload_config(args):
@@ -289,17 +315,23 @@ def run_b200(args):
                                   ws_sum, st), reps=3)
     sm3 = timed(lambda: _lib.call("dgb_block_gauss_seidel_pyamg", op, fine.d_rhs, xg, 0, 3, mode, 0, ctl0, ws_part,
                                   ws_sum, st), reps=2)
+    ctl0.zero_()
     chained = fine.d_chain is not None and mode == _lib.GS_LEXICOGRAPHIC
     t_pass_amortised = (sm3[0] - sm1[0]) / 4.0                   # one later pass of a symmetric sweep
-    t_first = sm1[0] - t_pass_amortised                          # first pass of a call (helper + chain when chained)
     peak, peak_src = measured_peak()
     kern = {}
+    # algorithmic bytes per launch
     ab_chain = N * (2 * b * b + 4 * b) * 8        # chain pass: 2 pre-multiplied blocks, c, d in; x, next c out
     ab_helper = N * (3 * b * b + 5 * b) * 8       # helper: Dinv + 2 blocks, rhs, x in; c, d (both streams) out
+    ab_entry = ab["residual"] + N * (b * b + 3 * b) * 8   # fused entry residual + helper: 5 blocks + Dinv; + c, d, d out
     rows = [("apply", k_apply, ab["apply"]), ("residual_norm", k_resid, ab["residual"]), ("gs_pass", k_gs, ab["gs_pass"])]
     if chained:
+        k_entry = timed(lambda: L.dgb_block_gs_entry_residual(__import__("ctypes").byref(op), _lib.ptr(fine.d_rhs),
+                                                              _lib.ptr(xg), 1, _lib.ptr(y), _lib.ptr(ws_part),
+                                                              _lib.ptr(ws_sum), st), reps=3)
         rows += [("gs_chain_pass", (t_pass_amortised, 1), ab_chain),
-                 ("gs_helper", (max(k_gs[0] - t_pass_amortised, 1e-6), 1), ab_helper)]
+                 ("gs_helper", (max(k_gs[0] - t_pass_amortised, 1e-6), 1), ab_helper),
+                 ("gs_entry_residual", k_entry, ab_entry)]
     else:
         rows += [("gs_pass_in_sweep", (t_pass_amortised, k_gs[1]), ab["gs_pass"])]
     for nm, (ms, nl), nbytes in rows:
@@ -307,72 +339,287 @@ def run_b200(args):
         kern[nm] = {"ms": ms, "launches": nl, "algorithmic_bytes": nbytes, "GB/s": gbs, "frac": gbs / peak}
     kern["smoother_symmetric_1it_ms"] = sm1[0]
     kern["smoother_symmetric_3it_ms"] = sm3[0]
-    # share of one V-cycle spent in each fine-level kernel family (reference schedule: 2 pre + 1 post symmetric
-    # iterations = 6 passes in 2 smoother calls; 5 residual evaluations, the restriction reuses the smoother's last)
-    n_res = 5 if args.check_residual else 1
-    fam = {"residual_norm": n_res * kern["residual_norm"]["ms"]}
+    # launches per V-cycle on the fine level, from the schedule the library runs (dgb_vcycle.cu, gs_pyamg in
+    # dgb_solve.cu): pre 2 + post 1 symmetric iterations = 6 passes in 2 smoother calls; with the residual tests
+    # each call opens with the fused entry residual (chained) or a plain residual, every iteration closes with a
+    # residual (3), and the restriction reuses the pre-smoother's last one
+    chk = bool(args.check_residual)
     if chained:
-        fam["gs_chain_pass"] = 6 * kern["gs_chain_pass"]["ms"]
-        fam["gs_helper"] = 2 * kern["gs_helper"]["ms"]
+        per_cycle = {"gs_chain_pass": 6, "residual_norm": 3 if chk else 1,
+                     "gs_entry_residual": 2 if chk else 0, "gs_helper": 0 if chk else 2}
     else:
-        fam["gs_pass"] = 6 * kern["gs_pass"]["ms"]
+        per_cycle = {"gs_pass": 6, "residual_norm": 5 if chk else 1}
+    fam = {nm: cnt * kern[nm]["ms"] for nm, cnt in per_cycle.items() if cnt}
     for nm, ms in fam.items():
+        kern[nm]["launches_per_vcycle"] = per_cycle[nm]
         kern[nm]["share_of_vcycle"] = ms / ms_per_step
     top = max(fam, key=fam.get)
     names = {"residual_norm": f"k_rows<{b}, residual> (r = rhs - A u and its norm, fine level)",
              "gs_chain_pass": f"k_gs_chain<{b}> (dependency chain of one lexicographic block-GS pass, fine level)",
-             "gs_helper": f"k_gs_helper<{b}> (dependency-free part of a block-GS pass, fine level)",
+             "gs_helper": f"k_gs_helper<{b}, false> (dependency-free part of a block-GS pass, fine level)",
+             "gs_entry_residual": f"k_gs_helper<{b}, true> (smoother entry residual fused with the dependency-free part)",
              "gs_pass": f"block_gs_pass(fine level, b={b}, mode={args.gs_mode})"}
-    # DRAM traffic of the dominant kernel from one `ncu --set full` capture of the same launch (profiles/), if there
-    # is one for this workload and kernel
-    traffic, traffic_src = None, None
-    tfile = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
-                         "r01_ncu_full_k_rows_b9_residual_summary.json")
-    if top == "residual_norm" and n == 2048 and p == 2 and os.path.exists(tfile):
+    # DRAM traffic per launch from the tracked `ncu --set full` summaries of the same kernels (profiles/)
+    traffic_tab = {}
+    tfile = os.path.join(REPO, "profiles", "r02_ncu_traffic.json")
+    if n == 2048 and p == 2 and os.path.exists(tfile):
         with open(tfile) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/" + os.path.basename(tfile)
+            traffic_tab = json.load(f)
+    tr = traffic_tab.get(top, {})
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": kern[top]["GB/s"], "peak": peak, "unit": "GB/s",
-                "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "share_of_vcycle": kern[top]["share_of_vcycle"],
-                "launches_per_call": kern[top]["launches"],
-                "algorithmic_bytes_per_launch_group": kern[top]["algorithmic_bytes"],
-                "other_kernels": {nm: {"frac": kern[nm]["frac"], "share_of_vcycle": kern[nm]["share_of_vcycle"]}
+                "frac": kern[top]["frac"], "traffic": tr.get("traffic_bytes_per_launch"),
+                "traffic_source": tr.get("source"), "peak_source": peak_src,
+                "share_of_vcycle": kern[top]["share_of_vcycle"], "launches_per_vcycle": per_cycle[top],
+                "ms_per_launch": kern[top]["ms"],
+                "algorithmic_bytes_per_launch": kern[top]["algorithmic_bytes"],
+                "selection": "largest launches_per_vcycle x ms_per_launch among the fine-level kernels (measured live)",
+                "other_kernels": {nm: {"frac": kern[nm]["frac"], "share_of_vcycle": kern[nm]["share_of_vcycle"],
+                                       "launches_per_vcycle": per_cycle[nm],
+                                       "traffic": traffic_tab.get(nm, {}).get("traffic_bytes_per_launch")}
                                   for nm in fam if nm != top}}
-    # V-cycle level traffic: reference schedule = 12 passes/level (+ transfers, ignored)
-    vbytes = 0
-    for g in d.grids[1:]:
+    # ---- V-cycle level traffic --------------------------------------------------------------
+    # bytes_min: per non-coarsest level 6 passes + 1 residual, coarsest 20 passes, + transfers
+    # bytes_moved: what this library's kernels have to move for the same cycle (chain passes stream 2 of the 5
+    # blocks; the residual tests of the reference's schedule are kept)
+    bytes_min = bytes_moved = 0
+    for li, g in enumerate(d.grids):
         bb = g.d_data.shape[1]
-        a_g = algorithmic_bytes(int(g.d_indices.numel()), g.Ni * g.Nj, bb)
-        vbytes += 6 * a_g["gs_pass"] + (6 if args.check_residual else 1) * a_g["residual"]
-    g0 = d.grids[0]
-    a_0 = algorithmic_bytes(int(g0.d_indices.numel()), g0.Ni * g0.Nj, g0.d_data.shape[1])
-    vbytes += 20 * a_0["gs_pass"] + (11 if args.check_residual else 0) * a_0["residual"]
-    vcycle_gbs = vbytes / (ms_per_step * 1e-3) / 1e9
+        Ng = g.Ni * g.Nj
+        a_g = algorithmic_bytes(int(g.d_indices.numel()), Ng, bb)
+        ch = g.d_chain is not None and mode == _lib.GS_LEXICOGRAPHIC
+        c_pass = Ng * (2 * bb * bb + 4 * bb) * 8 if ch else a_g["gs_pass"]
+        c_entry = a_g["residual"] + (Ng * (bb * bb + 3 * bb) * 8 if ch else 0)
+        if li == 0:
+            bytes_min += 20 * a_g["gs_pass"]
+            bytes_moved += 20 * c_pass + ((c_entry + 10 * a_g["residual"]) if chk else (Ng * (3 * bb * bb + 5 * bb) * 8 if ch else 0))
+        else:
+            bytes_min += 6 * a_g["gs_pass"] + a_g["residual"]
+            bytes_moved += 6 * c_pass + ((2 * c_entry + 3 * a_g["residual"]) if chk
+                                         else (a_g["residual"] + (2 * Ng * (3 * bb * bb + 5 * bb) * 8 if ch else 0)))
+            cg = d.grids[li - 1]
+            tb = 8 * (Ng * bb + cg.Ni * cg.Nj * cg.d_data.shape[1]) * 2 + 8 * Ng * bb      # restrict + prolong-add
+            bytes_min += tb
+            bytes_moved += tb
+    vc_t = ms_per_step * 1e-3
+    vcycle = {"bytes_min": bytes_min, "bytes_min_GBs": bytes_min / vc_t / 1e9, "frac_bytes_min": bytes_min / vc_t / 1e9 / peak,
+              "bytes_moved": bytes_moved, "bytes_moved_GBs": bytes_moved / vc_t / 1e9,
+              "frac_bytes_moved": bytes_moved / vc_t / 1e9 / peak,
+              "frac_bytes_min_of_nominal_8TBs": bytes_min / vc_t / 1e9 / 8000.0,
+              "normalised_residual_after_timed_cycles": res_after / res0,
+              "cycles_run": args.warmup + args.steps}
+    # device memory the hierarchy holds (operator, inverse diagonal blocks, smoother streams, vectors)
+    mem = {"data": 0, "dinv": 0, "gs_chain": 0, "gs_data": 0, "mailbox": 0, "vectors": 0}
+    for g in d.grids:
+        for key, t in (("data", g.d_data), ("dinv", g.d_dinv), ("gs_chain", g.d_chain), ("gs_data", g.d_gs),
+                       ("mailbox", g.d_mailbox)):
+            if t is not None:
+                mem[key] += t.numel() * t.element_size()
+        mem["vectors"] += 4 * g.Ni * g.Nj * g.d_data.shape[1] * 8
+    mem["total_GB"] = sum(v for v in mem.values()) / 1e9
+    mem["torch_allocated_GB"] = torch.cuda.memory_allocated() / 1e9
 
-    # ---- CPU baseline (oracle), bounded sample ----------------------------------------------
-    cpu = None
+    # ---- CPU baseline (oracle) on a bounded sample + parity of the GPU cycle on that sample ------------
+    cpu = parity = None
     if not args.no_cpu_baseline:
-        dt, sample_dofs, setup = cpu_reference_vcycle(args.cpu_sample, p, 2, 1)
-        cpu_val = (1.0 / dt) * (sample_dofs / n_dof)
-        cpu = {"value": cpu_val, "unit": "V-cycles/s", "cores": 1, "kind": "port",
-               "sample": f"oracle V-cycle on Rectangle {args.cpu_sample}x{args.cpu_sample} p={p} ({sample_dofs} DOFs, "
-                         f"{dt * 1e3:.0f} ms/cycle), scaled by DOFs to {n}x{n}; host has {os.cpu_count()} cores, "
-                         f"the reference path is single-threaded"}
+        dt, sample_dofs, setup, u_first = cpu_reference_vcycle(args.cpu_sample, p, 1, 1)
+        cpu = cpu_baseline_block(args, dt, sample_dofs, setup, n_dof)
+        m = args.cpu_sample
+        s2 = Settings(make_params(m, p, args.gs_mode, bool(args.check_residual)))
+        d2 = DGFEM(settings=s2, geometry=Geometry(None, s2, nodes=rectangle_nodes_file_order(m, p)),
+                   solve_multigrid=True, write_results=False)
+        f2 = d2.grids[-1]
+        u_gpu = d2.solver.multigrid_V_cycle(len(d2.grids), f2.RHS, np.zeros_like(f2.RHS))
+        err = float(np.abs(u_gpu - u_first).max() / np.abs(u_first).max())
+        parity = {"grid": f"{m}x{m}", "check": "u after one V-cycle from u=0, GPU vs oracle, max rel err",
+                  "rel_err": err, "tolerance": 1e-10, "ok": bool(err < 1e-10) if args.gs_mode == "lexicographic" else None}
+        del d2
 
     line = {"metric": "multigrid_vcycles_per_s", "value": value, "unit": "V-cycles/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kern,
-            "vcycle": {"algorithmic_bytes": vbytes, "GB/s": vcycle_gbs, "frac_of_peak": vcycle_gbs / peak,
-                       "normalised_residual_after_timed_cycles": res_after / res0,
-                       "cycles_run": args.warmup + args.steps},
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "kernels": kern, "vcycle": vcycle, "memory": mem,
             "apply_dof_per_s": n_dof / (k_apply[0] * 1e-3),
             "vcycle_dof_per_s": n_dof * value,
             "setup_s": setup_s, "assemble_s": d.timings.get("assemble"),
             "assembly_elements_per_s": sum(g.Ni * g.Nj for g in d.grids) / d.timings["assemble"]}
+    if args.p5_apply and n >= 1024:
+        # BASELINE's "operator-apply DOF/s (p=2,5)": the p=5 number at configs[3]'s size, in the same run
+        del d, solver, H, xg, y, rhs_k, u_k, r_k
+        torch.cuda.empty_cache()
+        try:
+            c4 = run_config_c4(1024, quick=True)
+            line["apply_dof_per_s_p5"] = c4["apply_dof_per_s"]
+            line["apply_p5"] = {k: c4[k] for k in ("config", "dofs", "b", "apply_ms", "apply_GBs", "apply_frac",
+                                                   "assemble_s", "assembly_elements_per_s")}
+        except Exception as e:                       # the headline line must not depend on the second workload
+            line["apply_p5"] = {"error": repr(e)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+def _lgl_line(edges, P):
+    from dg_multigrid_solver_b200.tables import gauss_lobatto_nodes
+    xi = gauss_lobatto_nodes(P + 1)
+    out = np.empty((len(edges) - 1) * P + 1)
+    for e in range(len(edges) - 1):
+        out[e * P:(e + 1) * P + 1] = edges[e] + (edges[e + 1] - edges[e]) * (xi + 1.0) / 2.0
+    return out
+
+
+def circle_nodes_file_order(n, P, r_in=0.1, r_out=1.0):
+    """CircleInCircle_{n}X{n}_nPoly{P}: i = angle (clockwise), j = radius with element widths
+    in geometric progression of ratio 10^(1/(n-1)); Plot3D file order [jl][il]."""
+    q = 10.0 ** (1.0 / (n - 1))
+    widths = (r_out - r_in) * (q - 1.0) / (q ** n - 1.0) * q ** np.arange(n)
+    redges = r_in + np.concatenate([[0.0], np.cumsum(widths)])
+    redges[-1] = r_out
+    th = _lgl_line(-2.0 * np.pi * np.arange(n + 1) / n, P)
+    rr = _lgl_line(redges, P)
+    x = np.cos(th)[None, :] * rr[:, None]
+    y = np.sin(th)[None, :] * rr[:, None]
+    x[:, -1], y[:, -1] = x[:, 0], y[:, 0]          # close the O-grid exactly (grid.py:56-57)
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+def _timed(fn, reps=3):
+    import torch
+    fn(); torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    c.record(); torch.cuda.synchronize()
+    return a.elapsed_time(c) / reps
+
+
+def run_config_c4(n=1024, quick=False):
+    """BASELINE.json configs[3]: CircleInCircle n x n nPoly5 (O-grid, sigma-mult 2), p=5 single level: assembly,
+    operator apply, block-Jacobi sweep, symmetric lexicographic block-GS iterations (36x36 blocks), and the
+    reference's `-s --smoother block_gauss_seidel_pyamg` run (100 iterations with residual tests).
+    quick: assembly + apply only."""
+    import torch
+    from dg_multigrid_solver_b200 import _lib
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.settings import Settings
+    peak, _ = measured_peak()
+    st = _lib.stream_ptr()
+    p = 5
+    prm = make_params(n, p, "lexicographic", True)
+    prm["grid"].update({"O grid": True, "circular": True, "filename": f"synthetic_CircleInCircle_{n}X{n}_nPoly5.xyz"})
+    prm["problem"]["SIP penalty parameter multiplier"] = 2.0
+    s = Settings(prm)
+    xn, yn = circle_nodes_file_order(n, p)
+    t0 = time.perf_counter()
+    d = DGFEM(settings=s, geometry=Geometry(None, s, nodes=(xn, yn)), solve_smoother=True,
+              smoother="block_gauss_seidel_pyamg", write_results=False)
+    torch.cuda.synchronize()
+    setup = time.perf_counter() - t0
+    g = d.grids[-1]
+    g.release_geometry()
+    N, b, nnzb = g.Ni * g.Nj, g.b, int(g.d_indices.numel())
+    ab = algorithmic_bytes(nnzb, N, b)
+    x = torch.randn(N * b, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    op = g.operator()
+    t_apply = _timed(lambda: _lib.call("dgb_bsr_apply", op, x, y, st))
+    out = {"config": f"C4 CircleInCircle {n}x{n} p=5 O-grid (BASELINE.json configs[3])", "elements": N, "dofs": N * b,
+           "b": b, "nnzb": nnzb, "operator_GB": nnzb * b * b * 8 / 1e9, "setup_s": setup,
+           "assemble_s": d.timings.get("assemble"), "assembly_elements_per_s": N / d.timings["assemble"],
+           "apply_ms": t_apply, "apply_GBs": ab["apply"] / t_apply / 1e6, "apply_frac": ab["apply"] / t_apply / 1e6 / peak,
+           "apply_dof_per_s": N * b / (t_apply * 1e-3)}
+    if quick:
+        return out
+    t_jac = _timed(lambda: _lib.call("dgb_block_relax_sweep", op, g.d_rhs, x, y, 1.0, st))
+    xg = torch.zeros_like(x)
+    L = _lib.load()
+    ctl = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    part = torch.zeros(L.dgb_partials_len(), dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def smoother(iters):      # the smoother as Solver.solve_smoother calls it, without its residual tests
+        _lib.call("dgb_block_gauss_seidel_pyamg", op, g.d_rhs, xg, 0, iters, 0, 0, ctl, part, ss, st)
+    t1 = _timed(lambda: smoother(1), reps=2)
+    t3 = _timed(lambda: smoother(3), reps=2)
+    t_gs = (t3 - t1) / 2.0                       # one symmetric iteration inside a longer call = 2 chain passes
+    # the reference's `-s --smoother block_gauss_seidel_pyamg` run: 100 symmetric iterations with residual tests
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d.solver.solve()
+    torch.cuda.synchronize()
+    t_s100 = time.perf_counter() - t0
+    chained = g.d_chain is not None
+    # bytes the pass kernels must move: a chained pass streams 2 pre-multiplied blocks + c, d, x, next c
+    pass_bytes = N * (2 * b * b + 4 * b) * 8 if chained else ab["gs_pass"]
+    out.update({"smoother_run_100_iterations_s": t_s100,
+                "block_jacobi_sweep_ms": t_jac, "block_jacobi_GBs": ab["gs_pass"] / t_jac / 1e6,
+                "block_jacobi_frac": ab["gs_pass"] / t_jac / 1e6 / peak,
+                "block_jacobi_dof_per_s": N * b / (t_jac * 1e-3),
+                "gs_first_symmetric_iteration_ms": t1, "gs_symmetric_iteration_ms": t_gs,
+                "gs_pass_bytes_moved": pass_bytes, "gs_pass_GBs": 2 * pass_bytes / t_gs / 1e6,
+                "gs_pass_frac": 2 * pass_bytes / t_gs / 1e6 / peak,
+                "gs_pass_GBs_on_survey_8d_bytes": 2 * ab["gs_pass"] / t_gs / 1e6,
+                "gs_sweep_dof_per_s": 2 * N * b / (t_gs * 1e-3), "device_error": L.dgb_device_error(1)})
+    return out
+
+
+def run_config_c5(n=1024):
+    """BASELINE.json configs[4]: Rectangle n x n nPoly2, Stokes local ordering (p_u=2, p_p=1): assembly + apply."""
+    import torch
+    from dg_multigrid_solver_b200 import _lib
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.settings import Settings
+    peak, _ = measured_peak()
+    st = _lib.stream_ptr()
+    prm = make_params(n, 2, "lexicographic", True)
+    prm["problem"]["type"] = "Stokes"
+    prm["problem"]["include pressure BC"] = False
+    prm["solution"]["p"]["polynomial degree"] = 1
+    prm["solution"]["ordering"] = "local"
+    s = Settings(prm)
+    xn, yn = rectangle_nodes_file_order(n, 2)
+    t0 = time.perf_counter()
+    d = DGFEM(settings=s, geometry=Geometry(None, s, nodes=(xn, yn)), solve_direct=True, write_results=False)
+    torch.cuda.synchronize()
+    setup = time.perf_counter() - t0
+    g = d.grids[-1]
+    N, b, nnzb = g.Ni * g.Nj, int(g.d_data.shape[1]), int(g.d_indices.numel())
+    ab = algorithmic_bytes(nnzb, N, b)
+    x = torch.randn(N * b, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    op = g.operator()
+    t_apply = _timed(lambda: _lib.call("dgb_bsr_apply", op, x, y, st))
+    return {"config": f"C5 Rectangle {n}x{n} Stokes p_u=2 p_p=1 local order (BASELINE.json configs[4])", "elements": N,
+            "dofs": N * b, "b": b, "nnzb": nnzb, "operator_GB": nnzb * b * b * 8 / 1e9, "setup_s": setup,
+            "assemble_s": d.timings.get("assemble"), "assembly_elements_per_s": N / d.timings["assemble"],
+            "apply_ms": t_apply, "apply_GBs": ab["apply"] / t_apply / 1e6, "apply_frac": ab["apply"] / t_apply / 1e6 / peak,
+            "apply_dof_per_s": N * b / (t_apply * 1e-3)}
+
+
+def run_other_config(args):
+    """--config c4 | c5: one JSON line in the bench contract (metric = operator-apply DOF/s of that configuration,
+    the configuration's other device-timed numbers beside it)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    n = args.size if args.size != 2048 else 1024
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    out = run_config_c4(n) if args.config == "c4" else run_config_c5(n)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    line = {"metric": "operator_apply_dof_per_s", "value": out["apply_dof_per_s"], "unit": "DOF/s", "n_gpus": 1,
+            "steps": 3, "warmup": 1, "ms_per_step": out["apply_ms"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": out["config"], "l2_policy": f"inputs larger than L2 ({out['operator_GB']:.1f} GB operator)"},
+            "clocks": clocks, "gpu_launches": 4,
+            "roofline": {"bound": "hbm", "kernel": f"k_rows<{out['b']}, apply>", "achieved": out["apply_GBs"], "peak": peak,
+                         "unit": "GB/s", "frac": out["apply_frac"], "traffic": None, "peak_source": peak_src},
+            "e2e": None, "cpu_baseline": None, "details": out}
     print(json.dumps(line), flush=True)
 
 
@@ -386,14 +633,20 @@ def main():
     ap.add_argument("--p", type=int, default=2)
     ap.add_argument("--gs-mode", default="lexicographic", choices=["lexicographic", "redblack", "slab_lexicographic"])
     ap.add_argument("--check-residual", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 = the V-cycle workload (BASELINE configs[2], default); c4 / c5 = configs[3] / configs[4]")
+    ap.add_argument("--p5-apply", type=int, default=1,
+                    help="also measure the p=5 operator apply (configs[3]'s operator, 1024^2) in the default run")
     ap.add_argument("--exact-multi", action="store_true",
                     help="N>1: keep the exact global lexicographic order (slabs sweep one after the other)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c3":
+        run_other_config(args)
     else:
         run_b200(args)
 

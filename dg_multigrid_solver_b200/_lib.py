@@ -75,6 +75,7 @@ SIGNATURES = {
     "dgb_fill_sentinel": (c_i32, [c_vp, c_i64, c_vp]),
     "dgb_dense_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_dense_solve": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_nodal_error": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_bsr_apply": (c_i32, [OP, c_vp, c_vp, c_vp]),
     "dgb_bsr_residual": (c_i32, [OP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),

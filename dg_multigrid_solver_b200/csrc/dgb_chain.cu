@@ -23,7 +23,8 @@
 // The sweep order, and therefore the result up to rounding of the re-associated products, is exactly the
 // reference's.  O-grids (periodic in i): the LAST element of a row has a third earlier neighbour, the row's first
 // element across the wrap; its pre-multiplied block lives in a small side array (one per row and direction) and
-// is applied by the fill/drain path of the chain kernel.  Grids periodic in j keep the row-pipelined kernel.
+// is staged in shared memory and applied by the fill/drain path of the chain kernel.  Grids periodic in j keep the
+// row-pipelined kernel.
 #include "dgb_async.cuh"
 #include "dgb_common.cuh"
 
@@ -38,7 +39,10 @@ extern int g_gs_variant;
 template <int B>
 struct ChainCfg {
     static constexpr int B2 = B * B;
-    static constexpr int P = B == 9 ? 3 : B == 16 ? 2 : 1;            // lanes per scalar row (each takes B/P columns)
+    // lanes per scalar row (each takes B/P columns).  b = 9: P = 3 / one element row per warp; P = 1 with three
+    // element rows per warp was measured in round 2 (profiles/r02_probe_chain_variants.md): its step is 1.8x longer
+    // (the shared-memory load rate of a lone warp, 8.4 cycles per LDS.128, bounds a step) and the pass 2.2 vs 1.76 ms
+    static constexpr int P = B == 9 ? 3 : B == 16 ? 2 : 1;
     static constexpr int CW = B / P;                                  // matrix columns per lane
     static constexpr int LPR = B * P;                                 // lanes per element row
     static constexpr int R = LPR > 32 ? 1 : 32 / LPR;                 // element rows per warp (b=36: k_gs_chain_big)
@@ -59,7 +63,9 @@ struct ChainCfg {
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
     static constexpr int WDEF = B == 9 ? 8 : B == 16 ? 5 : B <= 4 ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
-    static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : 0);
+    static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : ((RINGR * BP * 8) % 128) == 64 ? 2 : 0);
+    // O-grids: per warp, the wrap blocks of its R rows (staged once) and the rows' first new values
+    static constexpr int WRAPD = LPR > 32 ? 0 : R * (B2 + BP);
     static constexpr int WR = RING * BP + R * RRS;                    // ring doubles per warp: incoming + rows
     static constexpr int SCR = RING * BP + 64;                        // scratch doubles per CTA: dummy store targets (benign races)
     __host__ __device__ static constexpr int stage_d(int W) { return W * NS * R * CH * REC; }
@@ -68,7 +74,8 @@ struct ChainCfg {
     __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * WR; }
     __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * SCR; }
     __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * W * NS; }
-    __host__ __device__ static constexpr size_t smem(int W) { return o_prog(W) + sizeof(int) * (W + 1); }
+    __host__ __device__ static constexpr size_t o_wrap(int W) { return (o_prog(W) + sizeof(int) * (W + 1) + 15) & ~(size_t)15; }
+    __host__ __device__ static constexpr size_t smem(int W) { return o_wrap(W) + sizeof(double) * W * WRAPD; }
 };
 
 __device__ __forceinline__ bool chain_sentinel(double v) { return __double2hiint(v) == -1; }
@@ -82,6 +89,17 @@ __device__ __forceinline__ double lds1(uint32_t a) {
 __device__ __forceinline__ double2 lds2(uint32_t a) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+// volatile flavours: ptxas keeps volatile accesses in program order (the delivery test must precede the data loads)
+__device__ __forceinline__ double lds1v(uint32_t a) {
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds2v(uint32_t a) {
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts1(uint32_t a, double v) {
@@ -111,12 +129,56 @@ __device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<
         *any_sentinel = mx == 0xffffffffu;
     }
 }
+// the "not delivered" test of the fast path: every lane of an element row looks at the high word of ONE entry of
+// the slot (entry part*CW + r % CW: the lanes of a row cover all B entries), a warp vote does the rest
+__device__ __forceinline__ uint32_t lds_u32v(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// my part of one ring slot, volatile loads (ordered after the delivery test)
+template <int B>
+__device__ __forceinline__ void chain_load_vec_v(uint32_t a, double (&v)[ChainCfg<B>::VN]) {
+    constexpr int VN = ChainCfg<B>::VN;
+    if (VN % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < VN; c += 2) {
+            const double2 t = lds2v(a + c * 8);
+            v[c] = t.x;
+            v[c + 1 < VN ? c + 1 : c] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < VN; ++c) v[c] = lds1v(a + c * 8);
+    }
+}
 
 // my part of my rows of the two (negated) pre-multiplied blocks and my entries of c and d, from the staged record
 template <int B>
 struct ChainRow {
     static constexpr int VN = ChainCfg<B>::VN, P = ChainCfg<B>::P, CW = ChainCfg<B>::CW;
     double ml[CW], mu[CW], c, d;
+    // the same through volatile loads: ptxas keeps them behind the (volatile) loads of the ring slots
+    __device__ __forceinline__ void load_v(uint32_t rm, uint32_t rc) {
+        constexpr int B2 = B * B;
+        c = lds1v(rc);
+        d = lds1v(rc + B * 8);
+        constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
+        if (MV == 2) {
+#pragma unroll
+            for (int k = 0; k < CW; k += 2) {
+                const double2 m0 = lds2v(rm + (k / 2) * LS * 8), m1 = lds2v(rm + (B2 + (k / 2) * LS) * 8);
+                ml[k] = m0.x; ml[k + 1 < CW ? k + 1 : k] = m0.y;
+                mu[k] = m1.x; mu[k + 1 < CW ? k + 1 : k] = m1.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+                ml[k] = lds1v(rm + k * LS * 8);
+                mu[k] = lds1v(rm + (B2 + k * LS) * 8);
+            }
+        }
+    }
     __device__ __forceinline__ void load(uint32_t rm, uint32_t rc) {
         constexpr int B2 = B * B;
         c = lds1(rc);
@@ -141,7 +203,26 @@ struct ChainRow {
     // x = c - M_row x_prev - M_up x_up   (records hold the negated products); with P > 1 the partial sums of the
     // P lanes of a scalar row are added by shuffles and the result is valid in the lane with part == 0
     // extra: this lane's share of one more (negated) product, added before the lanes of a row are summed
-    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN], double extra = 0.0) const {
+    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN]) const {
+        if (P == 1) {
+            // four independent accumulators, c folded into the first product (no c + 0.0)
+            double a0 = fma(ml[0], p[0], c), a1 = CW > 1 ? ml[CW > 1 ? 1 : 0] * p[CW > 1 ? 1 : 0] : 0.0;
+            double a2 = mu[0] * u[0], a3 = CW > 1 ? mu[CW > 1 ? 1 : 0] * u[CW > 1 ? 1 : 0] : 0.0;
+#pragma unroll
+            for (int k = 2; k < CW; ++k) {
+                if (k & 1) {
+                    a1 = fma(ml[k], p[k], a1);
+                    a3 = fma(mu[k], u[k], a3);
+                } else {
+                    a0 = fma(ml[k], p[k], a0);
+                    a2 = fma(mu[k], u[k], a2);
+                }
+            }
+            return (a0 + a1) + (a2 + a3);
+        }
+        return eval(p, u, 0.0);
+    }
+    __device__ __forceinline__ double eval(const double (&p)[VN], const double (&u)[VN], double extra) const {
         if (P == 1) {
             double a0 = c + extra, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
@@ -377,6 +458,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     uint32_t out_w = lastg ? (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank)) + 8 * r
                            : cluster_map(scr, crank) + 8 * lane;
     const uint32_t po = (uint32_t)(part * CW * 8);                     // my columns inside a ring slot
+    const uint32_t co = (uint32_t)((part * CW + r % CW) * 8 + 4);      // high word of the slot entry I test for delivery
     const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
                                          : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
     uint32_t sen_w = (fin && first_row) ? in_b + 8 * r : scr + 8 * lane;         // row 0 hands the incoming slot back
@@ -387,16 +469,18 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
     asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
-    // O-grid: my entries of the block that couples the row's last element to its first one (wrapm[row][B2],
-    // lane-major like the record blocks), and the first element's new value (picked up one step after it is made)
-    constexpr bool PER_OK = B != 25;            // (b=25 has no registers to spare: its O-grid levels keep k_gs_rows)
-    constexpr int WN = PER_OK ? CW : 1;
-    const int per = PER_OK ? S_.per_i : 0;
-    double mw[WN], xf[WN];
-#pragma unroll
-    for (int k = 0; k < WN; ++k) {
-        mw[k] = per ? wrapm[(size_t)j * B2 + C::mat_offset(r, part * CW + k)] : 0.0;
-        xf[k] = 0.0;
+    // O-grid: the block that couples a row's last element to its first one (wrapm[row][B2], lane-major like the
+    // record blocks) is staged in shared memory once per band; the first element's new value is parked beside it
+    // one step after it is made and picked up again at the row's last element (fill/drain path only)
+    const int per = S_.per_i;
+    double *wrapw = reinterpret_cast<double *>(smem + C::o_wrap(W)) + (size_t)w * C::WRAPD;
+    double *xfw = wrapw + R * B2;
+    if (per) {
+        for (int q = lane; q < Rv * B2; q += 32) {
+            const int gg = q / B2;
+            wrapw[q] = wrapm[(size_t)(DIR > 0 ? j0 + gg : j0 - gg) * B2 + (q - gg * B2)];
+        }
+        __syncwarp();
     }
     // my entry of c in the OTHER direction's record of sweep index idx: a constant stride of -R records per step
     // (the opposite sweep visits the rows and the columns in reverse order)
@@ -470,17 +554,24 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
             asm volatile("" : "+r"(ua0), "+r"(ua), "+r"(pa0), "+r"(pa));
             asm volatile("" : "+r"(ow), "+r"(sw), "+r"(sm), "+r"(sc));
             asm volatile("" : "+l"(xp), "+l"(cop));
+            // software pipeline: the record of step k + 1 is read (plain shared-memory loads, the stage is complete)
+            // while the dependent arithmetic of step k waits for its operands
+            ChainRow<B> rows[2];
+            rows[0].load(sm, sc);
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const uint32_t uk = k == 0 ? ua0 : ua + k * S;     // slot of the row above
                 double u[VN], p[VN];
-                ChainRow<B> row;
-                bool bad;
-                chain_load_vec<B>(uk + po, u, &bad);
-                chain_load_vec<B>(k == 0 ? pa0 : pa + k * S, p, nullptr);
-                row.load(sm + k * KS, sc + k * KS);
-                const bool wait_up = __any_sync(FULL, bad);        // the neighbour band has not delivered yet?
+                // delivery test BEFORE the data: the lanes of a row test one entry each in ONE warp-wide load, so every
+                // entry seen delivered here is delivered in the (later) loads of u as well
+                const uint32_t hi_u = lds_u32v(uk + co);
+                chain_load_vec_v<B>(uk + po, u);
+                chain_load_vec_v<B>(k == 0 ? pa0 : pa + k * S, p);
+                if (k + 1 < CH) rows[(k + 1) & 1].load_v(sm + (k + 1) * KS, sc + (k + 1) * KS);
+                const ChainRow<B> &row = rows[k & 1];
                 double xnew = row.eval(p, u);
+                // the neighbour band has not delivered this column yet?  (rows above inside the warp always have)
+                const bool wait_up = __any_sync(FULL, hi_u == 0xffffffffu);
                 if (__builtin_expect(wait_up, 0)) {
                     if (!chain_wait_up<B>(uk, err)) return;
                     chain_load_vec<B>(uk + po, u, nullptr);
@@ -519,14 +610,15 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
                 ChainRow<B> row;
                 row.load(sm + k * KS, sc + k * KS);
                 double extra = 0.0;
-                if (PER_OK && per) {
-                    if (idx == 1) {                     // p holds the new value of the row's first element
+                if (per) {
+                    if (idx == 1 && r == 0) {           // p holds the new value of the row's first element
 #pragma unroll
-                        for (int q = 0; q < WN; ++q) xf[q] = p[q];
+                        for (int q = 0; q < CW; ++q) xfw[gq * BP + part * CW + q] = p[q];
                     }
                     if (idx == Ni - 1) {                // the wrap neighbour is an earlier element of the sweep
 #pragma unroll
-                        for (int q = 0; q < WN; ++q) extra = fma(mw[q], xf[q], extra);
+                        for (int q = 0; q < CW; ++q)
+                            extra = fma(wrapw[gq * B2 + C::mat_offset(r, part * CW + q)], xfw[gq * BP + part * CW + q], extra);
                     }
                 }
                 const double xnew = row.eval(p, u, extra);
@@ -983,9 +1075,8 @@ int g_chain_mask = 31;
 bool chain_supported(int b, int flags) {
     if (g_gs_variant == 9) return false;            // tuning: force the row-pipelined kernel
     const int bit = b == 4 ? 1 : b == 9 ? 2 : b == 16 ? 4 : b == 25 ? 8 : b == 36 ? 16 : 0;
-    // periodic in j (fully periodic grids) is not handled; b=25 has no registers left for the wrap block
-    return flags >= 0 && (flags & DGB_FLAG_PERIODIC_J) == 0 && !((flags & DGB_FLAG_PERIODIC_I) && b == 25) &&
-           (g_chain_mask & bit) != 0;
+    // periodic in j (fully periodic grids) is not handled
+    return flags >= 0 && (flags & DGB_FLAG_PERIODIC_J) == 0 && (g_chain_mask & bit) != 0;
 }
 // O-grids need three distinct elements per row (else the wrap neighbour coincides with the row neighbour)
 static bool chain_shape_ok(int Ni, int flags) { return !(flags & DGB_FLAG_PERIODIC_I) || Ni >= 3; }

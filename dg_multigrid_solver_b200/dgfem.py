@@ -152,31 +152,33 @@ class DGFEM:
             residual_0 = compute_Lp_norm(g.RHS, 2)
             self.residual_normalized = self.residual / residual_0
             if self.settings.problem.type == "Poisson":
-                self.u_nodal, self.u_exact_nodal = self._nodal_fields(g, d_u)
-                delta = (self.u_nodal - self.u_exact_nodal)
-                self.L1_error_u = float(delta.abs().mean().item())                      # dgfem.py:220
-                self.L2_error_u = float(torch.sqrt((delta * delta).mean()).item())     # dgfem.py:221
+                self.u_nodal, self.L1_error_u, self.L2_error_u = self._nodal_error(g, d_u)
         self.timings["postprocess"] = t.elapsed()
         if self.write_results and self.settings.problem.type == "Poisson":
+            if self.settings.get("visualization.export", False) and self.u_nodal is not None:   # dgfem.py:236-247
+                from .visualization import modal_to_vtk
+                self.solution_visualization_filepath = os.path.join(self.results_dir, "solution")
+                modal_to_vtk(self.solution_visualization_filepath, self, self.u_nodal, self.u_exact_nodes)
             with open(self.solution_summary_filepath, "a") as f:
                 f.write(f"Residual={self.residual}\nL1 error={self.L1_error_u}\nL2 error={self.L2_error_u}\n")
         return u_modal
 
-    def _nodal_fields(self, g, d_u):
-        """u at the geometry nodes of every element: V_DOF_grid @ u_e (dgfem.py:203-205) and the exact
-        solution there (dgfem.py:114); device tensors of shape [N, (Pg+1)^2] (node index a + N1*c)."""
+    def _nodal_error(self, g, d_u, want_nodal=True):
+        """dgfem.py:188-232 in one kernel (dgb_nodal_error): u at the geometry nodes of every element
+        (V_DOF_grid @ u_e, [N, (Pg+1)^2], node index a + N1*c), minus the exact solution there (evaluated once per
+        grid node by the MMS expression), and the L1 / L2 error norms.  Returns (u_nodal or None, L1, L2)."""
         torch = _lib.require_cuda()
         T = g.tables
-        Vg = torch.from_numpy(np.ascontiguousarray(T.V_DOF_grid)).cuda()               # [ng, b]
-        u_nodal = d_u.view(-1, T.b) @ Vg.T
-        xn, yn = self.geometry.device_nodes()                                           # [jl, il]
-        Pg, N1 = g.P_grid, g.P_grid + 1
-        e = torch.arange(g.Ni * g.Nj, device="cuda")
-        i, j = e % g.Ni, e // g.Ni
-        a = torch.arange(N1, device="cuda")
-        n_i = (i[:, None] * Pg + a[None, :])                                            # [N, N1] along i
-        n_j = (j[:, None] * Pg + a[None, :])
-        flat = (n_j[:, :, None] * g.il + n_i[:, None, :]).reshape(g.Ni * g.Nj, N1 * N1)  # c major, a minor
-        mms = PoissonMMS(self.settings)
-        u_exact = mms.solution(xn.reshape(-1)[flat], yn.reshape(-1)[flat])
-        return u_nodal, u_exact
+        Vg = torch.from_numpy(np.ascontiguousarray(T.V_DOF_grid, dtype=np.float64)).cuda()      # [ng, b]
+        ng = int(Vg.shape[0])
+        xn, yn = self.geometry.device_nodes()                                                    # [jl, il]
+        exact = PoissonMMS(self.settings).solution(xn, yn).contiguous()                         # dgfem.py:114
+        N = g.Ni * g.Nj
+        u_nodal = torch.empty((N, ng), dtype=torch.float64, device="cuda") if want_nodal else None
+        partials = torch.zeros(_lib.load().dgb_partials_len(), dtype=torch.float64, device="cuda")
+        sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+        _lib.call("dgb_nodal_error", Vg, ng, int(T.b), int(g.P_grid), int(g.Ni), int(g.Nj), int(g.il),
+                  d_u.contiguous(), exact, u_nodal, partials, sums, _lib.stream_ptr())
+        s1, s2 = (float(v) for v in sums.cpu())
+        self.u_exact_nodes = exact
+        return u_nodal, s1 / (N * ng), float(np.sqrt(s2 / (N * ng)))                             # dgfem.py:220-221

@@ -393,6 +393,17 @@ int dgb_assemble_rhs_stokes(const dgb_tables *t_uu, const dgb_tables *t_pu, cons
                             const double *g_p, int32_t Ni, int32_t Nj, double nu, double sigma,
                             double gamma, int32_t flags, double *rhs, void *stream);
 
+/* ---- post-processing --------------------------------------------------------------------------
+ * replaces the per-element loop of DGFEM.solve (dgfem/dgfem.py:188-232): u_nodal[e] = V_DOF_grid @ u_e at the
+ * element's (Pg+1)^2 geometry nodes (node a_i + (Pg+1)*a_j, i fastest), minus the exact solution there, and
+ *   sums[0] = sum |u_nodal - u_exact|,  sums[1] = sum (u_nodal - u_exact)^2   over all N*ng element nodes
+ * (L1 = sums[0]/(N ng), L2 = sqrt(sums[1]/(N ng)), dgfem.py:220-221).
+ * V_grid[ng][b] (Grid.initialize_interpolation's V_DOF_grid); exact_nodes[jl][il]: the exact solution at the grid
+ * nodes in Plot3D file order; u_nodal[N][ng] optional (NULL = sums only); partials: dgb_partials_len() doubles. */
+int dgb_nodal_error(const double *V_grid, int32_t ng, int32_t b, int32_t Pg, int32_t Ni, int32_t Nj, int32_t il,
+                    const double *u, const double *exact_nodes, double *u_nodal, double *partials, double *sums,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -457,3 +457,40 @@ def test_chained_gauss_seidel_kernel_ogrid(Ni, Nj, P):
         _chained_gs_checks(grid, Ni, Nj, L)
     finally:
         L.dgb_set_kernel_path(300 + CHAIN_MASK_DEFAULT)
+
+
+def test_direct_solve_and_export():
+    """`-d` (Solver.solve_directly, dgfem/solver.py:56-59: spsolve on the assembled system) through the dense
+    inverse kernels, against scipy on the GPU-assembled matrix; the fused post-processing kernel
+    (dgb_nodal_error) against the plain evaluation; the `.vts` export of DGFEM.solve."""
+    import scipy.sparse.linalg as splin
+    import torch
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.mms import PoissonMMS
+    case = CASES["rect8_h24"]
+    s = make_settings(case)
+    s.update_setting("visualization.export", True)
+    d = DGFEM(settings=s, geometry=Geometry(grid_path(case), s), solve_direct=True, write_results=True)
+    u = d.solve()
+    fine = d.grids[-1]
+    ref = splin.spsolve(fine.BSR.tocsr(), fine.RHS)
+    assert rel_err(u, ref) < 1e-11
+    assert d.residual_normalized < 1e-12
+    # post-processing: V_DOF_grid @ u_e at the element nodes, exact solution there, L1 / L2 (dgfem.py:203-221)
+    T = fine.tables
+    un = u.reshape(-1, T.b) @ np.asarray(T.V_DOF_grid).T
+    assert rel_err(d.u_nodal.cpu().numpy(), un) < 1e-13
+    xn, yn = (t.cpu().numpy() for t in d.geometry.device_nodes())
+    N1, Pg = fine.P_grid + 1, fine.P_grid
+    ex = PoissonMMS(s).solution(torch.from_numpy(xn).cuda(), torch.from_numpy(yn).cuda()).cpu().numpy()
+    delta = []
+    for e in range(fine.Ni * fine.Nj):
+        i, j = e % fine.Ni, e // fine.Ni
+        blk = ex[j * Pg:j * Pg + N1, i * Pg:i * Pg + N1]          # [c, a]
+        delta.append(un[e] - blk.reshape(-1))
+    delta = np.concatenate(delta)
+    assert abs(d.L1_error_u - np.abs(delta).mean()) < 1e-13
+    assert abs(d.L2_error_u - np.sqrt((delta ** 2).mean())) < 1e-13
+    vts = d.solution_visualization_filepath + ".vts"
+    assert os.path.exists(vts) and os.path.getsize(vts) > fine.Ni * fine.Nj * N1 * N1 * 8 * 6

@@ -114,23 +114,63 @@ def test_mms_fields_host():
 
 
 def test_full_size_config_generators_follow_the_shipped_grid_rule():
-    """tools/bench_configs.py and bench.py generate the C3/C4 grids with their own code (the product side may
-    not import the oracle); they must agree with the oracle's restatement of the shipped grids' rule."""
-    import importlib.util
-    import os
-    import sys
+    """bench.py generates the C3/C4 grids with its own code (the product side may not import the oracle); they
+    must agree with the oracle's restatement of the shipped grids' rule."""
     from dgoracle import plot3d
-    from helpers import REPO
     import bench
     x, y = plot3d.rectangle_nodes(6, 6, 2)
     xn, yn = bench.rectangle_nodes_file_order(6, 2)
     assert np.array_equal(xn, x.T) and np.array_equal(yn, y.T)
-    # bench_configs imports torch-only product modules at import time; load just its generator
-    src = open(os.path.join(REPO, "tools", "bench_configs.py")).read()
-    ns = {}
-    start = src.index("def lgl_line")
-    end = src.index("def timed")
-    exec("import numpy as np\nfrom dg_multigrid_solver_b200.tables import gauss_lobatto_nodes\n" + src[start:end], ns)
     xc, yc = plot3d.circle_in_circle_nodes(8, 8, 3)
-    xg, yg = ns["circle_nodes_file_order"](8, 3)
+    xg, yg = bench.circle_nodes_file_order(8, 3)
     assert np.allclose(xg, xc.T, rtol=0, atol=1e-15) and np.allclose(yg, yc.T, rtol=0, atol=1e-15)
+
+
+def test_plot3d_writer_round_trip(tmp_path):
+    """visualization.write_plot3d writes what Geometry.read (dgfem/grid.py:26-63) reads; a shipped grid is
+    reproduced byte for byte."""
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.visualization import write_plot3d
+    for name in ("c1", "c2"):
+        case = CASES[name]
+        geo = Geometry(grid_path(case), make_settings(case))
+        out = write_plot3d(str(tmp_path / f"{name}.xyz"), geo.xn, geo.yn)
+        assert open(out, "rb").read() == open(grid_path(case), "rb").read()
+        geo2 = Geometry(out, make_settings(case))
+        assert np.array_equal(geo2.xn, geo.xn) and np.array_equal(geo2.yn, geo.yn)
+
+
+def test_vts_export_layout(tmp_path, monkeypatch):
+    """elements_to_vtk: the reference's point layout (dgfem/visualization.py:67-117: element nodes side by side,
+    Ni*N1 x Nj*N1 points, i fastest) in a VTK XML StructuredGrid with raw appended data."""
+    import re
+    import struct
+    from dg_multigrid_solver_b200.visualization import element_node_arrays, elements_to_vtk, nodal_to_elements
+    monkeypatch.chdir(tmp_path)
+    Ni, Nj, Pg = 3, 2, 2
+    N1 = Pg + 1
+    xl = np.linspace(0.0, 3.0, Ni * Pg + 1)
+    yl = np.linspace(0.0, 1.0, Nj * Pg + 1)
+    xn, yn = np.meshgrid(xl, yl)                        # file order [jl][il]
+    x_el, y_el = element_node_arrays(xn, yn, Ni, Nj, Pg)
+    assert x_el.shape == (Ni, Nj, N1, N1)
+    assert x_el[2, 1, 1, 0] == xl[2 * Pg + 1] and y_el[2, 1, 1, 2] == yl[1 * Pg + 2]
+    u_nodal = (np.arange(Ni * Nj)[:, None] * 100 + np.arange(N1 * N1)[None, :]).astype(float)   # [N, ng]
+    phi = nodal_to_elements(u_nodal, Ni, Nj, Pg)
+    assert phi[1, 1, 2, 0] == (1 * Ni + 1) * 100 + 2 and phi[0, 1, 0, 1] == (1 * Ni) * 100 + N1
+    path = elements_to_vtk("sol", x_el, y_el, "Poisson", {"phi": phi, "abs_error_phi": np.abs(phi)})
+    raw = open(path, "rb").read()
+    head, tail = raw.split(b'<AppendedData encoding="raw">\n_')
+    nx, ny = Ni * N1, Nj * N1
+    assert f'WholeExtent="0 {nx - 1} 0 {ny - 1} 0 0"'.encode() in head
+    offs = [int(v) for v in re.findall(rb'offset="(\d+)"', head)]
+    names = re.findall(rb'Name="(\w+)"', head)
+    assert names == [b"phi", b"abs_error_phi", b"points"] and sorted(offs)[0] == 0
+    npts = struct.unpack("<Q", tail[:8])[0]
+    assert npts == nx * ny * 3 * 8
+    pts = np.frombuffer(tail[8:8 + npts], dtype="<f8").reshape(ny, nx, 3)
+    assert pts[0, 1, 0] == xl[1] and pts[N1, 0, 1] == yl[Pg] and np.all(pts[:, :, 2] == 0)
+    o = offs[names.index(b"phi")]
+    nb = struct.unpack("<Q", tail[o:o + 8])[0]
+    v = np.frombuffer(tail[o + 8:o + 8 + nb], dtype="<f8").reshape(ny, nx)
+    assert v[1 * N1 + 0, 1 * N1 + 2] == phi[1, 1, 2, 0]
