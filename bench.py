@@ -329,6 +329,12 @@ def run_b200(args):
         k_entry = timed(lambda: L.dgb_block_gs_entry_residual(__import__("ctypes").byref(op), _lib.ptr(fine.d_rhs),
                                                               _lib.ptr(xg), 1, _lib.ptr(y), _lib.ptr(ws_part),
                                                               _lib.ptr(ws_sum), st), reps=3)
+        # residual right after a pass, from the records the pass left (k_residual_rec): after 1 backward pass
+        _lib.call("dgb_block_gauss_seidel_pyamg", op, fine.d_rhs, xg, 0, 1, mode, 0, ctl0, ws_part, ws_sum, st)
+        k_rr = timed(lambda: L.dgb_block_gs_residual_after_pass(__import__("ctypes").byref(op), _lib.ptr(xg), -1, _lib.ptr(y),
+                                                                _lib.ptr(ws_part), _lib.ptr(ws_sum), None, st), reps=3)
+        ab_rr = N * (3 * b * b + 5 * b) * 8          # 2 pre-multiplied blocks + c, d; diagonal block; x, r
+        rows += [("residual_after_pass", k_rr, ab_rr)]
         rows += [("gs_chain_pass", (t_pass_amortised, 1), ab_chain),
                  ("gs_helper", (max(k_gs[0] - t_pass_amortised, 1e-6), 1), ab_helper),
                  ("gs_entry_residual", k_entry, ab_entry)]
@@ -345,7 +351,9 @@ def run_b200(args):
     # residual (3), and the restriction reuses the pre-smoother's last one
     chk = bool(args.check_residual)
     if chained:
-        per_cycle = {"gs_chain_pass": 6, "residual_norm": 3 if chk else 1,
+        rec_res = b in (4, 9, 16)
+        per_cycle = {"gs_chain_pass": 6, "residual_after_pass": 3 if (chk and rec_res) else 0,
+                     "residual_norm": (0 if rec_res else 3) if chk else 1,
                      "gs_entry_residual": 2 if chk else 0, "gs_helper": 0 if chk else 2}
     else:
         per_cycle = {"gs_pass": 6, "residual_norm": 5 if chk else 1}
@@ -358,6 +366,7 @@ def run_b200(args):
              "gs_chain_pass": f"k_gs_chain<{b}> (dependency chain of one lexicographic block-GS pass, fine level)",
              "gs_helper": f"k_gs_helper<{b}, false> (dependency-free part of a block-GS pass, fine level)",
              "gs_entry_residual": f"k_gs_helper<{b}, true> (smoother entry residual fused with the dependency-free part)",
+             "residual_after_pass": f"k_residual_rec<{b}> (residual test of a smoother iteration, from the pass's records)",
              "gs_pass": f"block_gs_pass(fine level, b={b}, mode={args.gs_mode})"}
     # DRAM traffic per launch from the tracked `ncu --set full` summaries of the same kernels (profiles/)
     traffic_tab = {}
@@ -389,12 +398,13 @@ def run_b200(args):
         ch = g.d_chain is not None and mode == _lib.GS_LEXICOGRAPHIC
         c_pass = Ng * (2 * bb * bb + 4 * bb) * 8 if ch else a_g["gs_pass"]
         c_entry = a_g["residual"] + (Ng * (bb * bb + 3 * bb) * 8 if ch else 0)
+        c_res = Ng * (3 * bb * bb + 5 * bb) * 8 if (ch and bb in (4, 9, 16)) else a_g["residual"]
         if li == 0:
             bytes_min += 20 * a_g["gs_pass"]
-            bytes_moved += 20 * c_pass + ((c_entry + 10 * a_g["residual"]) if chk else (Ng * (3 * bb * bb + 5 * bb) * 8 if ch else 0))
+            bytes_moved += 20 * c_pass + ((c_entry + 10 * c_res) if chk else (Ng * (3 * bb * bb + 5 * bb) * 8 if ch else 0))
         else:
             bytes_min += 6 * a_g["gs_pass"] + a_g["residual"]
-            bytes_moved += 6 * c_pass + ((2 * c_entry + 3 * a_g["residual"]) if chk
+            bytes_moved += 6 * c_pass + ((2 * c_entry + 3 * c_res) if chk
                                          else (a_g["residual"] + (2 * Ng * (3 * bb * bb + 5 * bb) * 8 if ch else 0)))
             cg = d.grids[li - 1]
             tb = 8 * (Ng * bb + cg.Ni * cg.Nj * cg.d_data.shape[1]) * 2 + 8 * Ng * bb      # restrict + prolong-add

@@ -87,6 +87,7 @@ SIGNATURES = {
     "dgb_block_gs_pass": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_pass_seq": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_gs_entry_residual": (c_i32, [OP, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_block_gs_residual_after_pass": (c_i32, [OP, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_block_gs_colour": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "dgb_block_relax_sweep": (c_i32, [OP, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),

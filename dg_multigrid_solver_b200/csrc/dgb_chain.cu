@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(HelperCfg<B>::NT, RES ? 6 : 8)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
             double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
-            double *partials) {
+            double *partials, int x_zero /* x == 0 (coarse-level initial guess, solver.py:171): no block is read */) {
     constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
     if (skip != nullptr && *skip != 0) return;
     __shared__ double s_rsum[EPB * B];
@@ -915,7 +915,7 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             // O-grid: the last element of the row meets the (already updated) first one across the wrap
             const int e_wrap = (S_.per_i && i == (dir > 0 ? Ni - 1 : 0)) ? e - dir * (Ni - 1) : -1;
             double acc = 0.0, acc_chain = 0.0;
-            for (int jj = indptr[e]; jj < indptr[e + 1]; ++jj) {
+            for (int jj = x_zero ? indptr[e + 1] : indptr[e]; jj < indptr[e + 1]; ++jj) {
                 const int col = indices[jj];
                 // RES (entry of a smoother call): neighbours in ghost rows are left to the edge kernel of the pass
                 // that follows (dgb_block_gs_pass_seq), which sees the halo values of that moment
@@ -956,6 +956,113 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
         const double t = block_sum<HelperCfg<B>::NT>(sumsq, s_red);
         if (threadIdx.x == 0) partials[blockIdx.x] = t;
     }
+}
+
+// ---- residual after a pass, from the record stream -------------------------------------------------------
+// After a pass in direction D the records of direction -D hold, for every element e,
+//     c_e = Dinv_e (rhs_e - sum_{n before e in D order} A_en x_n)        (what the next, opposite pass starts from)
+// and the two pre-multiplied blocks of e's predecessors in -D order, i.e. of the neighbours that come AFTER e in D
+// order.  Hence   Dinv_e r_e = c_e + M_row x_(row-pred) + M_up x_(up-pred) [+ M_wrap x_first] - x_e   and
+//     r_e = A_ee (that)                                                   (r = rhs - A x, dgfem/relaxation.py:208)
+// from 2 b^2 + 2 b record doubles plus the diagonal block, instead of all five blocks of the row: the residual
+// test after every smoother iteration streams 0.64 of the bytes (b = 9).  Same mathematics as rhs - A x; the
+// rounding differs (products with Dinv A instead of A), at the level the chained kernel's own already does.
+// One thread per scalar row; a CTA stages TE consecutive records in shared memory with coalesced 16-byte loads.
+template <int B>
+struct ResRecCfg {
+    static constexpr int TE = (256 / B) > 0 ? (256 / B) : 1;            // records per tile
+    static constexpr int NT = ((TE * B + 31) / 32) * 32;
+    // staged records | rho | x of the element, of its row predecessor and of its up predecessor
+    static constexpr size_t smem = sizeof(double) * ((size_t)TE * ChainCfg<B>::REC + 4 * TE * B);
+};
+
+template <int B>
+__global__ void __launch_bounds__(ResRecCfg<B>::NT)
+k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm, const double *__restrict__ data,
+               const double *__restrict__ x, Stencil S_, int dirp /* direction of the records = -D */,
+               const int32_t *__restrict__ skip, double *r_out, double *partials) {
+    using C = ChainCfg<B>;
+    constexpr int TE = ResRecCfg<B>::TE, NT = ResRecCfg<B>::NT, REC = C::REC, R = C::R, B2 = B * B;
+    if (skip != nullptr && *skip != 0) return;
+    extern __shared__ __align__(16) double s_dyn[];
+    double *s_rec = s_dyn;                       // [TE][REC]
+    double *s_rho = s_dyn + (size_t)TE * REC;    // [TE][B]
+    double *s_x = s_rho + TE * B;                // [3][TE][B]: x_e, x_row-pred, x_up-pred (zero when absent)
+    __shared__ double s_red[32];
+    const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
+    // work item = (band, tile of TE consecutive records of that band): 32-bit index arithmetic
+    const unsigned per_band = (unsigned)(Ni + R - 1) * R;                 // records of a band
+    const unsigned tiles_band = (per_band + TE - 1) / TE;
+    const unsigned nbands = (unsigned)((nrows + R - 1) / R);
+    const unsigned nitems = nbands * tiles_band;
+    const int el = threadIdx.x / B, r = threadIdx.x - el * B;
+    double sumsq = 0.0;
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const unsigned band = item / tiles_band;
+        const unsigned q0 = (item - band * tiles_band) * TE;              // first record of the tile inside the band
+        const int cnt = (int)(per_band - q0 < (unsigned)TE ? per_band - q0 : (unsigned)TE);
+        {   // stage the tile (REC is even: 16-byte pieces), four loads in flight per thread
+            const double2 *src = reinterpret_cast<const double2 *>(rec + ((size_t)band * per_band + q0) * REC);
+            double2 *dst = reinterpret_cast<double2 *>(s_rec);
+            const int n2 = cnt * (REC / 2);
+            int t = threadIdx.x;
+            for (; t + 3 * NT < n2; t += 4 * NT) {
+                const double2 v0 = __ldcs(src + t), v1 = __ldcs(src + t + NT), v2 = __ldcs(src + t + 2 * NT),
+                              v3 = __ldcs(src + t + 3 * NT);
+                dst[t] = v0; dst[t + NT] = v1; dst[t + 2 * NT] = v2; dst[t + 3 * NT] = v3;
+            }
+            for (; t < n2; t += NT) dst[t] = __ldcs(src + t);
+        }
+        long long e = -1;
+        int i = 0, j = 0;
+        if (el < cnt) {
+            const unsigned rem = q0 + (unsigned)el;
+            const int t = (int)(rem / R), g = (int)(rem - (unsigned)t * R);
+            const int sr = (int)band * R + g, idx = t - g;
+            if (sr < nrows && idx >= 0 && idx < Ni) {
+                j = dirp > 0 ? S_.ja0 + sr : S_.ja1 - 1 - sr;
+                i = dirp > 0 ? idx : Ni - 1 - idx;
+                e = (long long)j * Ni + i;
+            }
+        }
+        if (e >= 0) {
+            const bool has_row = (i - dirp >= 0 && i - dirp < Ni), has_up = S_.active(j - dirp);
+            s_x[el * B + r] = x[e * B + r];
+            s_x[(TE + el) * B + r] = has_row ? x[(e - dirp) * B + r] : 0.0;
+            s_x[(2 * TE + el) * B + r] = has_up ? x[(e - (long long)dirp * Ni) * B + r] : 0.0;
+        }
+        __syncthreads();
+        if (e >= 0) {
+            const double *m = s_rec + (size_t)el * REC;
+            const double *xr = s_x + (TE + el) * B, *xu = s_x + (2 * TE + el) * B;
+            double a0 = m[2 * B2 + r] - s_x[el * B + r], a1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < B; ++c) {
+                a0 = fma(m[C::mat_offset(r, c)], xr[c], a0);
+                a1 = fma(m[B2 + C::mat_offset(r, c)], xu[c], a1);
+            }
+            if (S_.per_i && i == (dirp > 0 ? Ni - 1 : 0)) {       // the row's last element in record order: wrap block
+                const double *w = wrapm + (size_t)j * B2;
+                const double *xf = x + (e - (long long)dirp * (Ni - 1)) * B;
+                for (int c = 0; c < B; ++c) a1 = fma(w[C::mat_offset(r, c)], xf[c], a1);
+            }
+            s_rho[el * B + r] = a0 + a1;
+        }
+        __syncthreads();
+        if (e >= 0) {
+            // the diagonal block of row e sits at row_start + (number of smaller columns)
+            int c5[5], rk[5];
+            S_.cols(i, j, c5);
+            slot_ranks(c5, rk);
+            const double *d = data + ((size_t)(S_.row_start(i, j) + rk[0]) * B + r) * B;
+            const double res = row_dot<B>(d, s_rho + el * B);
+            if (r_out != nullptr) r_out[e * B + r] = res;
+            sumsq = fma(res, res, sumsq);
+        }
+        __syncthreads();
+    }
+    const double tsum = block_sum<NT>(sumsq, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tsum;
 }
 
 // ---- slabs: the c a chain pass leaves for the opposite direction lacks the terms of neighbours in ghost rows
@@ -1178,7 +1285,7 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
     }
     if (!have_c && g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
         k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
-                                                      S_, dir, skip, nullptr, nullptr);
+                                                      S_, dir, skip, nullptr, nullptr, 0);
         DGB_LAUNCH_OK();
     }
     if (g_gs_variant == 21) return 0;
@@ -1192,7 +1299,7 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
 // sums of squares; *grid_out = number of partials written
 template <int B>
 static int helper_residual_t(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
-                             double *partials, int *grid_out, cudaStream_t st) {
+                             double *partials, int *grid_out, cudaStream_t st, bool x_zero) {
     using H = HelperCfg<B>;
     const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
     double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
@@ -1202,19 +1309,61 @@ static int helper_residual_t(const dgb_operator *op, const double *rhs, const do
     if (grid > sm_count() * 6) grid = sm_count() * 6;       // one wave at the occupancy __launch_bounds__ asks for
     if (grid > kMaxPartials) grid = kMaxPartials;
     k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
-                                                 dir, nullptr, r, partials);
+                                                 dir, nullptr, r, partials, x_zero ? 1 : 0);
     DGB_LAUNCH_OK();
     *grid_out = grid;
     return 0;
 }
-int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
-                             double *partials, int *grid_out, cudaStream_t st) {
+// residual after a pass in direction `last_dir` from the records of the opposite direction; *grid_out partials
+template <int B>
+static int residual_rec_t(const dgb_operator *op, const double *x, int last_dir, double *r, double *partials,
+                          int *grid_out, const int32_t *skip, cudaStream_t st) {
+    using C = ChainCfg<B>;
+    using RC = ResRecCfg<B>;
+    static bool configured = false;
+    static int occ = 1;
+    if (!configured) {
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_residual_rec<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC::smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_residual_rec<B>, RC::NT, RC::smem) != cudaSuccess || occ < 1)
+            occ = 1;
+        if (occ > 8) occ = 8;
+        configured = true;
+    }
+    const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
+    const int dirp = -last_dir;
+    const double *rec = op->gs_chain + (dirp > 0 ? 0 : chain_dir_len(B, S_));
+    const double *wrapm = op->gs_chain + 2 * chain_dir_len(B, S_) + (dirp > 0 ? 0 : (long long)S_.Nj * C::B2);
+    const long long per_band = (long long)(S_.Ni + C::R - 1) * C::R;
+    const long long nbands = (S_.ja1 - S_.ja0 + C::R - 1) / C::R;
+    long long grid = nbands * ((per_band + RC::TE - 1) / RC::TE);
+    if (grid > (long long)sm_count() * occ) grid = (long long)sm_count() * occ;
+    if (grid > kMaxPartials) grid = kMaxPartials;
+    k_residual_rec<B><<<(int)grid, RC::NT, RC::smem, st>>>(rec, wrapm, op->data, x, S_, dirp, skip, r, partials);
+    DGB_LAUNCH_OK();
+    *grid_out = (int)grid;
+    return 0;
+}
+// block sizes the record residual is compiled for (shared-memory tile of 256/b records)
+bool chain_residual_supported(int b) { return b == 4 || b == 9 || b == 16; }
+int gs_chain_residual(const dgb_operator *op, const double *x, int last_dir, double *r, double *partials,
+                      int *grid_out, const int32_t *skip, cudaStream_t st) {
     switch (op->b) {
-    case 4: return helper_residual_t<4>(op, rhs, x, dir, r, partials, grid_out, st);
-    case 9: return helper_residual_t<9>(op, rhs, x, dir, r, partials, grid_out, st);
-    case 16: return helper_residual_t<16>(op, rhs, x, dir, r, partials, grid_out, st);
-    case 25: return helper_residual_t<25>(op, rhs, x, dir, r, partials, grid_out, st);
-    case 36: return helper_residual_t<36>(op, rhs, x, dir, r, partials, grid_out, st);
+    case 4: return residual_rec_t<4>(op, x, last_dir, r, partials, grid_out, skip, st);
+    case 9: return residual_rec_t<9>(op, x, last_dir, r, partials, grid_out, skip, st);
+    case 16: return residual_rec_t<16>(op, x, last_dir, r, partials, grid_out, skip, st);
+    }
+    set_error("gs_chain_residual: unsupported block size b=%d", op->b);
+    return 2;
+}
+
+int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
+                             double *partials, int *grid_out, cudaStream_t st, bool x_zero) {
+    switch (op->b) {
+    case 4: return helper_residual_t<4>(op, rhs, x, dir, r, partials, grid_out, st, x_zero);
+    case 9: return helper_residual_t<9>(op, rhs, x, dir, r, partials, grid_out, st, x_zero);
+    case 16: return helper_residual_t<16>(op, rhs, x, dir, r, partials, grid_out, st, x_zero);
+    case 25: return helper_residual_t<25>(op, rhs, x, dir, r, partials, grid_out, st, x_zero);
+    case 36: return helper_residual_t<36>(op, rhs, x, dir, r, partials, grid_out, st, x_zero);
     }
     set_error("gs_chain_helper_residual: unsupported block size b=%d", op->b);
     return 2;
@@ -1291,7 +1440,7 @@ static int chain_pass_big(const dgb_operator *op, const double *rhs, double *x, 
     }
     if (!have_c && g_gs_variant != 22) {
         k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
-                                                      S_, dir, skip, nullptr, nullptr);
+                                                      S_, dir, skip, nullptr, nullptr, 0);
         DGB_LAUNCH_OK();
     }
     if (g_gs_variant == 21) return 0;

@@ -398,7 +398,11 @@ int gs_chain_pass(const dgb_operator *op, const double *rhs, double *x, int dir,
                   cudaStream_t st);
 bool chain_c_recurrence(int flags);
 int gs_chain_helper_residual(const dgb_operator *op, const double *rhs, const double *x, int dir, double *r,
-                             double *partials, int *grid_out, cudaStream_t st);
+                             double *partials, int *grid_out, cudaStream_t st, bool x_zero = false);
+bool chain_residual_supported(int b);
+int gs_chain_residual(const dgb_operator *op, const double *x, int last_dir, double *r, double *partials,
+                      int *grid_out, const int32_t *skip, cudaStream_t st);
+extern int g_gs_variant;
 
 // kernels that need the closed-form DG stencil (k_gs_rows)
 static bool use_stream(const dgb_operator *op) {
@@ -423,7 +427,7 @@ namespace dgb {
 // for the restriction instead of evaluating the same residual again (dgfem/solver.py:150).
 int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direction, int32_t max_iterations,
              int32_t mode, int32_t check_residual, dgb_smoother_ctl *ctl, double *partials, double *sumsq,
-             double *r_keep, void *stream, void *event_after_last_pass) {
+             double *r_keep, void *stream, void *event_after_last_pass, bool u_is_zero) {
     int rc = check_op(op);
     if (rc) return rc;
     DGB_ARG(ctl && partials && sumsq);
@@ -431,6 +435,11 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
     const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
     DGB_ARG(op->dinv && rhs && u);
     int last_dir = 0;      // direction of the previous lexicographic pass of this call (u untouched since)
+    // every pass of this call runs in the chained kernel with the c-recurrence (no ghost rows): the records of the
+    // opposite direction are complete after each pass
+    const bool chained_loop = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
+                              op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
+                              chain_supported(op->b, op->stencil) && chain_c_recurrence(op->stencil);
     if (check_residual) {
         const int first_dir = direction >= 0 ? +1 : -1;
         const bool chained = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
@@ -439,7 +448,8 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         if (chained) {
             // the entry residual shares its block reads with the dependency-free part of the first pass
             int grid = 1;
-            rc = gs_chain_helper_residual(op, rhs, u, first_dir, r_keep, partials, &grid, (cudaStream_t)stream);
+            rc = gs_chain_helper_residual(op, rhs, u, first_dir, r_keep, partials, &grid, (cudaStream_t)stream,
+                                          u_is_zero && g_gs_variant != 42);
             if (rc) return rc;
             k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, nullptr);
             DGB_LAUNCH_OK();
@@ -466,8 +476,18 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         if (it == max_iterations - 1 && event_after_last_pass != nullptr)       // u is final from here on
             DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)event_after_last_pass, (cudaStream_t)stream));
         if (check_residual) {
-            rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, skip, stream);
-            if (rc) return rc;
+            // after a chained pass the opposite direction's records hold everything the residual needs but the
+            // diagonal block: 2 b^2 + 2 b doubles per element instead of 5 b^2 (k_residual_rec, dgb_chain.cu)
+            if (chained_loop && last_dir != 0 && chain_residual_supported(op->b) && g_gs_variant != 41) {
+                int grid = 1;
+                rc = gs_chain_residual(op, u, last_dir, r_keep, partials, &grid, skip, (cudaStream_t)stream);
+                if (rc) return rc;
+                k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, skip);
+                DGB_LAUNCH_OK();
+            } else {
+                rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, skip, stream);
+                if (rc) return rc;
+            }
             rc = dgb_smoother_check(ctl, sumsq, n, stream);
             if (rc) return rc;
         }
@@ -640,6 +660,23 @@ int dgb_block_gs_entry_residual(const dgb_operator *op, const double *rhs, const
     rc = gs_chain_helper_residual(op, rhs, x, first_direction, r, partials, &grid, st);
     if (rc) return rc;
     k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, nullptr);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_block_gs_residual_after_pass(const dgb_operator *op, const double *x, int32_t last_direction, double *r,
+                                     double *partials, double *sumsq, const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(x && partials && sumsq && (last_direction == 1 || last_direction == -1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(use_stream(op) && op->gs_chain != nullptr && op->gs_mailbox != nullptr && chain_supported(op->b, op->stencil) &&
+          chain_c_recurrence(op->stencil) && chain_residual_supported(op->b)))
+        return DGB_UNSUPPORTED;
+    int grid = 1;
+    rc = gs_chain_residual(op, x, last_direction, r, partials, &grid, skip, st);
+    if (rc) return rc;
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
     DGB_LAUNCH_OK();
     return 0;
 }

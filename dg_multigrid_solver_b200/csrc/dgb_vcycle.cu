@@ -14,7 +14,7 @@ namespace dgb {
 // (dgfem/solver.py:143-147,196)
 static int smooth(const dgb_level &L, int smoother, int direction, double omega, const dgb_vcycle_opts &o,
                   int iterations, dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream,
-                  bool *have_residual = nullptr, void *u_final_event = nullptr) {
+                  bool *have_residual = nullptr, void *u_final_event = nullptr, bool u_is_zero = false) {
     if (have_residual) *have_residual = false;
     if (iterations <= 0 || smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG) {
         // no in-smoother hook: the event is recorded by the caller after the smoother returns
@@ -27,10 +27,11 @@ static int smooth(const dgb_level &L, int smoother, int direction, double omega,
     case DGB_SMOOTHER_BLOCK_GS_PYAMG:
         if (have_residual && o.check_residual) {
             *have_residual = true;
-            return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream);
+            return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream,
+                            nullptr, u_is_zero);
         }
         return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
-                        nullptr, stream, u_final_event);
+                        nullptr, stream, u_final_event, u_is_zero);
     case DGB_SMOOTHER_BLOCK_JACOBI: {
         // relaxation.py:123-150: iteration 1 is Jacobi into a fresh buffer, then `u = u_new`
         // aliases the two, so the remaining iterations are in-place forward sweeps.
@@ -53,8 +54,10 @@ static int smooth(const dgb_level &L, int smoother, int direction, double omega,
     }
 }
 
+// u_zero: this level's iterate was just zeroed (solver.py:171) -- its first smoother call need not read the operator
+// for its entry residual (r = rhs) and first right-hand sides (c = Dinv rhs): same bits, a sixth of the bytes
 static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream, bool top = false) {
+                  double *partials, double *sumsq, void *stream, bool top = false, bool u_zero = false) {
     const dgb_level &L = lv[k];
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
@@ -65,21 +68,23 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
         return rc;
     }
     if (k == 0) {   // solver.py:201-204
-        rc = smooth(L, L.smoother, L.direction, L.omega, o, o.coarse_iterations, ctl + k, partials, sumsq, stream, nullptr, ev);
+        rc = smooth(L, L.smoother, L.direction, L.omega, o, o.coarse_iterations, ctl + k, partials, sumsq, stream, nullptr, ev,
+                    u_zero);
         if (rc == 0 && ev != nullptr && L.smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG)
             DGB_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, st));
         return rc;
     }
     const dgb_level &C = lv[k - 1];
     bool have_r = false;
-    if ((rc = smooth(L, L.smoother, L.direction, L.omega, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r)))
+    if ((rc = smooth(L, L.smoother, L.direction, L.omega, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r,
+                     nullptr, u_zero)))
         return rc;
     // residual = RHS - BSR @ u (solver.py:150); the pre-smoother's last residual test already evaluated exactly
     // this vector (same kernel, same inputs), so it is not computed twice
     if (!have_r && (rc = dgb_bsr_residual(&L.op, L.rhs, L.u, L.r, partials, sumsq, nullptr, stream))) return rc;
     if ((rc = dgb_restrict(C.transfer_kind, C.R, C.nc, C.nf, C.op.Ni, C.op.Nj, L.r, C.rhs, stream))) return rc;
     DGB_CUDA_OK(cudaMemsetAsync(C.u, 0, sizeof(double) * (size_t)C.op.Ni * C.op.Nj * C.op.b, st));   // solver.py:171
-    if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream))) return rc;
+    if ((rc = vcycle(lv, k - 1, o, ctl, partials, sumsq, stream, false, true))) return rc;
     if ((rc = dgb_prolong_add(C.transfer_kind, C.P, C.nc, C.nf, C.op.Ni, C.op.Nj, C.u, L.u, stream))) return rc;
     rc = smooth(L, L.post_smoother, L.post_direction, L.post_omega, o, L.post_iterations, ctl + k, partials, sumsq,
                 stream, nullptr, ev);

@@ -188,6 +188,14 @@ int dgb_block_gs_entry_residual(const dgb_operator *h_op, const double *rhs, con
                                 int32_t first_direction, double *r, double *partials, double *sumsq,
                                 void *stream);
 
+/* Residual right after a chained lexicographic pass (direction last_direction) on the same rhs, x untouched since:
+ * r = rhs - A x (r may be NULL) and *sumsq = sum r^2, evaluated from the record stream the pass left behind plus the
+ * diagonal blocks (2 b^2 + 2 b + b^2 doubles per element instead of the 5 blocks of dgb_bsr_residual).  Replaces
+ * the residual test of every smoother iteration (dgfem/relaxation.py:208).  Returns DGB_UNSUPPORTED (nothing
+ * launched) when the operator has no chained kernel, lives on a slab with ghost rows, or b is not 4, 9 or 16. */
+int dgb_block_gs_residual_after_pass(const dgb_operator *h_op, const double *x, int32_t last_direction, double *r,
+                                     double *partials, double *sumsq, const int32_t *skip, void *stream);
+
 /* One colour class of the 2-colour sweep: rows with ((i + j + shift) & 1) == colour are relaxed in place.
  * `shift` carries the global row parity of a slab so that all ranks colour the global grid alike; the
  * caller exchanges halos between the two colours. */

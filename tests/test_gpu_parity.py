@@ -416,6 +416,34 @@ def _chained_gs_checks(grid, Ni, Nj, L):
         assert np.abs(got[0] - ref).max() <= 1e-12 * scale, (direction, np.abs(got[0] - ref).max() / scale)
     # the mailbox is all-sentinel again after the passes
     assert bool((grid.d_mailbox.view(torch.int64) == -1).all())
+    # residual right after a pass, evaluated from the records the pass left (k_residual_rec), against rhs - A x
+    from dg_multigrid_solver_b200 import _lib
+    from dg_multigrid_solver_b200.relaxation import bsr_apply, residual_norm
+    import ctypes
+    op = grid.operator()
+    st = _lib.stream_ptr()
+    d_rhs = torch.from_numpy(rhs).cuda()
+    part = torch.zeros(L.dgb_partials_len(), dtype=torch.float64, device="cuda")
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for sweeps in ([1], [-1], [1, -1], [1, -1, 1]):
+        d_x = torch.from_numpy(x0).cuda()
+        prev = 0
+        for sw in sweeps:
+            _lib.call("dgb_block_gs_pass_seq", op, d_rhs, d_x, sw, prev, None, st)
+            prev = sw
+        r_rec = torch.full_like(d_x, float("nan"))
+        rc = L.dgb_block_gs_residual_after_pass(ctypes.byref(op), _lib.ptr(d_x), prev, _lib.ptr(r_rec), _lib.ptr(part),
+                                                _lib.ptr(ss), None, st)
+        if rc == _lib.UNSUPPORTED:
+            assert b not in (4, 9, 16)
+            break
+        assert rc == 0
+        ss_rec = float(ss.item())
+        ss_ref, r_ref = residual_norm(grid, d_rhs, d_x, want_residual=True)
+        scale = float(torch.maximum(d_rhs.abs().max(), bsr_apply(grid, d_x).abs().max()))
+        assert float((r_rec - r_ref).abs().max()) <= 1e-12 * scale, (sweeps, float((r_rec - r_ref).abs().max()) / scale)
+        assert abs(ss_rec - float(ss_ref.item())) <= 1e-11 * max(float(ss_ref.item()), scale * scale * 1e-6)
+    assert L.dgb_device_error(1) == 0
 
 
 def test_vcycle_result_copied_out_on_second_stream():
