@@ -49,13 +49,27 @@ class VcycleOpts(ctypes.Structure):
                 ("coarse_solver", c_i32), ("u_final_event", c_vp), ("coarse_inverse", c_vp)]
 
 
+class SlabLevel(ctypes.Structure):
+    """dgb_slab_level (include/dgb200.h)."""
+    _fields_ = [("lev", Level), ("u_block", c_vp), ("ghost_lo", c_i32), ("ghost_hi", c_i32),
+                ("colour_shift", c_i32), ("pad", c_i32), ("n_global", c_i64)]
+
+
+class SlabOpts(ctypes.Structure):
+    """dgb_slab_opts (include/dgb200.h)."""
+    _fields_ = [("gs_mode", c_i32), ("check_residual", c_i32), ("link_kind", c_i32), ("link_nc", c_i32),
+                ("link_nf", c_i32), ("link_Ni_c", c_i32), ("link_rows_c", c_i32), ("n_coarse", c_i32),
+                ("link_R", c_vp), ("link_P", c_vp), ("link_rhs_local", c_vp),
+                ("coarse_levels", ctypes.POINTER(Level)), ("coarse_ctl", c_vp), ("coarse_opts", VcycleOpts)]
+
+
 class TablesDesc(ctypes.Structure):
     _fields_ = [("Pg", c_i32), ("p", c_i32), ("nq1", c_i32), ("cf", c_i32)] + \
         [(n, c_vp) for n in ("h_V", "h_Vr", "h_Vs", "h_w2", "h_w1", "h_Vf", "h_Vrf", "h_Vsf",
                              "h_GX", "h_GR", "h_GS", "h_FX", "h_FR", "h_FS", "h_sub_vol", "h_sub_face")]
 
 
-GS_LEXICOGRAPHIC, GS_REDBLACK = 0, 1
+GS_LEXICOGRAPHIC, GS_REDBLACK, GS_SLAB_LEXICOGRAPHIC = 0, 1, 2
 TRANSFER_P, TRANSFER_H = 1, 2
 SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_seidel": 2}
 FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV, FLAG_GHOST_LO, FLAG_GHOST_HI = 1, 2, 4, 8, 16
@@ -75,9 +89,21 @@ SIGNATURES = {
     "dgb_fill_sentinel": (c_i32, [c_vp, c_i64, c_vp]),
     "dgb_dense_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_dense_solve": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "dgb_comm_create": (c_i32, [c_i32, c_i32, c_i64, ctypes.POINTER(c_vp)]),
+    "dgb_comm_handle_bytes": (c_i32, []),
+    "dgb_comm_export": (c_i32, [c_vp, c_vp]),
+    "dgb_comm_connect": (c_i32, [c_vp, c_vp]),
+    "dgb_comm_arena": (c_vp, [c_vp, ctypes.POINTER(c_i64)]),
+    "dgb_comm_error": (c_i32, [c_vp, c_i32]),
+    "dgb_comm_destroy": (None, [c_vp]),
+    "dgb_halo_exchange": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "dgb_allreduce_sum": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i64, c_vp]),
+    "dgb_allgather": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "dgb_vcycle_slab": (c_i32, [c_vp, ctypes.POINTER(SlabLevel), c_i32, ctypes.POINTER(SlabOpts), c_vp, c_vp, c_vp, c_vp]),
     "dgb_nodal_error": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_bsr_apply": (c_i32, [OP, c_vp, c_vp, c_vp]),
     "dgb_bsr_residual": (c_i32, [OP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_bsr_residual_colour": (c_i32, [OP, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dgb_block_diag_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),

@@ -34,7 +34,8 @@ int sm_count() {
 // ---------------------------------------------------------------------------------------
 // element selection for the relaxation kernels
 struct Sel {
-    int mode;   // 0: all elements; 1: colour class (i+j)&1 == sel; 2: anti-diagonal i+j == sel
+    int mode;   // 0: all elements; 1: colour class (i+j)&1 == sel; 2: anti-diagonal i+j == sel;
+                // 3: colour class, compact: one item per pair (2m, 2m+1) of a row, every item has work
     int sel;
     int Ni, Nj;
     int i_lo;   // mode 2: first i on the diagonal
@@ -47,8 +48,21 @@ __device__ __forceinline__ int sel_element(const Sel &s, int idx) {
         const int i = idx % s.Ni, j = idx / s.Ni;
         return (((i + j + s.i_lo) & 1) == s.sel) ? idx : -1;
     }
+    if (s.mode == 3) {     // item = (row j, pair m): the element of the pair with (i + j + shift) & 1 == sel
+        const int np = (s.Ni + 1) >> 1;
+        const int j = idx / np, m = idx - j * np;
+        const int i = 2 * m + ((s.sel + j + s.i_lo) & 1);
+        return i < s.Ni ? j * s.Ni + i : -1;
+    }
     const int i = s.i_lo + idx;
     return (s.sel - i) * s.Ni + i;
+}
+// mode 3: the other element of the item's pair (the colour that is not selected), -1 if outside the row
+__device__ __forceinline__ int sel_partner(const Sel &s, int idx) {
+    const int np = (s.Ni + 1) >> 1;
+    const int j = idx / np, m = idx - j * np;
+    const int i = 2 * m + 1 - ((s.sel + j + s.i_lo) & 1);
+    return i < s.Ni ? j * s.Ni + i : -1;
 }
 
 enum { MODE_APPLY = 0, MODE_RESIDUAL = 1, MODE_RELAX = 2 };
@@ -106,6 +120,10 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
         const int idx = tile * EPB + el;
         int e = -1;
         if (lane_ok && idx < sel.count) e = sel_element(sel, idx);
+        if (MODE == MODE_RESIDUAL && sel.mode == 3 && lane_ok && idx < sel.count && writer && x_out != nullptr) {
+            const int ep = sel_partner(sel, idx);  // a row of the colour relaxed last: its residual is zero (to rounding)
+            if (ep >= 0 && indptr[ep] != indptr[ep + 1]) x_out[(size_t)ep * B + r] = 0.0;
+        }
         double acc = 0.0;
         if (e >= 0) {
             const int j0 = indptr[e], j1 = indptr[e + 1];
@@ -416,6 +434,8 @@ static int check_op(const dgb_operator *op) {
 }  // namespace dgb
 
 extern "C" {
+int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const double *x, double *r, int32_t relaxed,
+                            int32_t shift, double *partials, double *sumsq, const int32_t *skip, void *stream);
 static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
                               const int32_t *skip, cudaStream_t st, bool have_c = false);
 }
@@ -462,6 +482,10 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         if (rc) return rc;
     }
     const int32_t *skip = check_residual ? &ctl->skip : nullptr;
+    // 2-colour mode: relaxing a colour twice in a row with nothing in between recomputes the same values bit for bit
+    // (x_e = Dinv_e (rhs_e - sum A x_other colour)), so the second of two adjacent passes over one colour is dropped:
+    // a symmetric iteration 0,1 | 1,0 runs 0,1,0 and the next one starts at 1
+    int last_colour = -1;
     for (int it = 0; it < max_iterations; ++it) {
         for (int dir = +1; dir >= -1; dir -= 2) {
             if ((dir > 0 && direction < 0) || (dir < 0 && direction > 0)) continue;
@@ -469,7 +493,12 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
                 rc = ::lexicographic_pass(op, rhs, u, 1.0, dir, skip, (cudaStream_t)stream, last_dir == -dir);
                 last_dir = dir;
             } else {
-                rc = dgb_block_gs_pass(op, rhs, u, dir, mode, skip, stream);
+                for (int k = 0; k < 2 && rc == 0; ++k) {
+                    const int colour = dir > 0 ? k : 1 - k;
+                    if (colour == last_colour) continue;
+                    rc = dgb_block_gs_colour(op, rhs, u, colour, 0, skip, stream);
+                    last_colour = colour;
+                }
             }
             if (rc) return rc;
         }
@@ -484,6 +513,9 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
                 if (rc) return rc;
                 k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, skip);
                 DGB_LAUNCH_OK();
+            } else if (mode == DGB_GS_REDBLACK && last_colour >= 0 && op->stencil >= 0) {
+                rc = dgb_bsr_residual_colour(op, rhs, u, r_keep, last_colour, 0, partials, sumsq, skip, stream);
+                if (rc) return rc;
             } else {
                 rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, skip, stream);
                 if (rc) return rc;
@@ -536,6 +568,26 @@ int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x,
     int grid = 1;
     Sel sel{0, 0, N, 1, 0, N};
     DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
+                   k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
+                       op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
+    DGB_LAUNCH_OK();
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+// Residual after a 2-colour pass that relaxed colour `relaxed` last: those rows satisfy their equations (their
+// residual is rounding noise, written as zero), only the rows of the other colour are evaluated -- half the traffic.
+int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const double *x, double *r, int32_t relaxed,
+                            int32_t shift, double *partials, double *sumsq, const int32_t *skip, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(x && rhs && partials && sumsq && (relaxed == 0 || relaxed == 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = op->Ni * op->Nj;
+    int grid = 1;
+    Sel sel{3, 1 - relaxed, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj};
+    DGB_DISPATCH_B(op->b, grid = rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
                    k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
                        op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
     DGB_LAUNCH_OK();
@@ -628,7 +680,7 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
-            Sel sel{1, colour, op->Ni, op->Nj, 0, N};
+            Sel sel{3, colour, op->Ni, op->Nj, 0, ((op->Ni + 1) / 2) * op->Nj};
             rc = relax_launch(op, rhs, x, x, 1.0, sel, skip, st);
             if (rc) return rc;
         }
@@ -686,7 +738,7 @@ int dgb_block_gs_colour(const dgb_operator *op, const double *rhs, double *x, in
     int rc = check_op(op);
     if (rc) return rc;
     DGB_ARG(op->dinv && rhs && x && (colour == 0 || colour == 1));
-    Sel sel{1, colour, op->Ni, op->Nj, shift & 1, op->Ni * op->Nj};
+    Sel sel{3, colour, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj};
     return relax_launch(op, rhs, x, x, 1.0, sel, skip, (cudaStream_t)stream);
 }
 

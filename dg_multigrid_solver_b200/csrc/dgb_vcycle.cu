@@ -93,6 +93,12 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     return rc;
 }
 
+// the same cycle for the slab driver (dgb_comm.cu): the replicated coarse hierarchy below the distributed levels
+int vcycle_entry(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoother_ctl *ctl, double *partials,
+                 double *sumsq, void *stream, bool u_zero) {
+    return vcycle(lv, k, o, ctl, partials, sumsq, stream, false, u_zero);
+}
+
 }  // namespace dgb
 
 extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,

@@ -13,6 +13,15 @@ the edge rows of its neighbours, so each level carries ONE ghost element row per
                         the rest of the V-cycle with the single-GPU driver (dgb_vcycle) and scatters the
                         correction back (north_star: "coarsest level gathered to one GPU")
 
+Two transports for the same schedule:
+  native (default on one GPU per rank)   the whole V-cycle is ONE call into libdgb200 (dgb_vcycle_slab): halo
+                        exchange, norm reduction and the coarse gather are kernels that store straight into the
+                        peers' memory over NVLink (CUDA IPC mapped arenas, dgb_comm_*); the levels below the
+                        distributed ones are replicated on every rank (all-gather instead of gather + scatter).
+                        Only `redblack` and `slab_lexicographic` run natively.
+  torch.distributed     NCCL send/recv + all_reduce sequenced from Python (also the gloo path of the tests, and the
+                        exact `lexicographic` pipeline)
+
 Smoother orderings across slabs (`solver.b200.gs mode`):
   lexicographic        exact global lexicographic order: slab g sweeps after it received slab g-1's edge
                        row (a pipeline across ranks: exact, no parallel speed-up of the sweep itself)
@@ -190,6 +199,164 @@ class DistributedSolver:
         self.c_rows = rows0 // 2 if self.kind0 == _lib.TRANSFER_H else rows0
         self.c_Ni = g0.Ni // 2 if self.kind0 == _lib.TRANSFER_H else g0.Ni
         self.c_rhs = torch.zeros(self.c_rows * self.c_Ni * self.bc, dtype=torch.float64, device="cuda")
+        self.native, self.comm = False, None
+        self._graph, self._graph_failed, self._native_calls = None, False, 0
+        self.graph_launches = self.graph_replays = 0
+
+    # ---- native transport (peer memory, dgb_comm_* / dgb_vcycle_slab) ---------------------------------
+    @staticmethod
+    def _arena_tensor(ptr, n):
+        """float64 CUDA tensor view of n doubles at device address ptr (arena memory owned by libdgb200)."""
+        torch = _lib.require_cuda()
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(raw, device="cuda")
+
+    def enable_native(self):
+        """Move the iterates of the distributed levels into a peer-mapped arena and describe the hierarchy to
+        dgb_vcycle_slab.  Needs the replicated coarse hierarchy on EVERY rank (build_distributed(replicate=True))."""
+        import torch
+        import torch.distributed as dist
+        if self.gs_mode not in ("redblack", "slab_lexicographic"):
+            raise NotImplementedError("the native slab V-cycle runs `redblack` and `slab_lexicographic`")
+        if self.coarse is None:
+            raise RuntimeError("native slab V-cycle: this rank has no replicated coarse hierarchy")
+        L = _lib.load()
+        al = lambda nbytes: (int(nbytes) + 255) & ~255      # noqa: E731
+        blocks, off = [], 0
+        for g in self.grids:
+            rows = g.Nj - g.ghost_lo - g.ghost_hi
+            nb = (rows + 2) * g.Ni * g.b * 8
+            blocks.append((off, rows))
+            off += al(nb)
+        chunk = self.c_rows * self.c_Ni * self.bc
+        gather_off = off
+        off += al(self.world * chunk * 8)
+        comm = ctypes.c_void_p()
+        _lib.check(L.dgb_comm_create(self.rank, self.world, off, ctypes.byref(comm)), "dgb_comm_create")
+        hb = L.dgb_comm_handle_bytes()
+        mine = (ctypes.c_ubyte * hb)()
+        _lib.check(L.dgb_comm_export(comm, mine), "dgb_comm_export")
+        h = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(h) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(allh, h, group=self.group)
+        else:
+            allh = [h]
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        _lib.check(L.dgb_comm_connect(comm, blob), "dgb_comm_connect")
+        nbytes = ctypes.c_int64()
+        base = L.dgb_comm_arena(comm, ctypes.byref(nbytes))
+        self.comm, self._arena_base = comm, base
+        # iterates -> arena blocks [ghost below | owned | ghost above]
+        n = len(self.grids)
+        levels = (_lib.SlabLevel * n)()
+        self._keep = []
+        for k, g in enumerate(self.grids):
+            boff, rows = blocks[k]
+            row = g.Ni * g.b
+            blk = base + boff
+            u_new = self._arena_tensor(blk + (1 - g.ghost_lo) * row * 8, g.Ni * g.Nj * g.b)
+            u_new.copy_(self.vec[k][1])
+            rhs, _, r = self.vec[k]
+            self.vec[k] = (rhs, u_new, r)
+            SL = levels[k]
+            lev = SL.lev
+            lev.op = self.ops[k]
+            lev.rhs, lev.u, lev.r = rhs.data_ptr(), u_new.data_ptr(), r.data_ptr()
+            pre, post = self.sched[k]
+            for sm in (pre, post):
+                if sm.smoother != "block_gauss_seidel_pyamg":
+                    raise NotImplementedError("the native slab V-cycle smooths with block_gauss_seidel_pyamg")
+            directions = {"symmetric": 0, "forward": 1, "backward": -1}
+            lev.smoother = lev.post_smoother = _lib.SMOOTHER_IDS["block_gauss_seidel_pyamg"]
+            lev.direction, lev.post_direction = directions[pre.direction], directions[post.direction]
+            lev.pre_iterations, lev.post_iterations = int(pre.iterations), int(post.iterations)
+            lev.omega, lev.post_omega = float(pre.relaxation_factor), float(post.relaxation_factor)
+            if k < n - 1:               # transfer between this level (coarse side) and level k + 1: operators index k + 1
+                R, P = self.dR[k + 1], self.dP[k + 1]
+                lev.R, lev.P = R.data_ptr(), P.data_ptr()
+                lev.nc, lev.nf = int(R.shape[0]), int(R.shape[1])
+                lev.transfer_kind = _lib.TRANSFER_H if self.types[k + 1] == "geometric" else _lib.TRANSFER_P
+            SL.u_block = blk
+            SL.ghost_lo, SL.ghost_hi = int(g.ghost_lo), int(g.ghost_hi)
+            SL.colour_shift = int(self._colour_shift(g)) & 1
+            SL.n_global = int(self.n_owned[k] * self.world)
+        # replicated hierarchy: its top level's rhs is the all-gather destination
+        H = self.coarse.hierarchy()
+        top = H["n"] - 1
+        gather_ptr = base + gather_off
+        H["levels"][top].rhs = gather_ptr
+        self._coarse_rhs = self._arena_tensor(gather_ptr, self.world * chunk)
+        opts = _lib.SlabOpts()
+        opts.gs_mode = _lib.GS_REDBLACK if self.gs_mode == "redblack" else _lib.GS_SLAB_LEXICOGRAPHIC
+        opts.check_residual = 1 if self.check else 0
+        opts.link_kind = self.kind0
+        opts.link_nc, opts.link_nf = int(self.dR[0].shape[0]), int(self.dR[0].shape[1])
+        opts.link_Ni_c, opts.link_rows_c = int(self.c_Ni), int(self.c_rows)
+        opts.n_coarse = H["n"]
+        opts.link_R, opts.link_P = self.dR[0].data_ptr(), self.dP[0].data_ptr()
+        opts.link_rhs_local = self.c_rhs.data_ptr()
+        opts.coarse_levels = ctypes.cast(H["levels"], ctypes.POINTER(_lib.Level))
+        opts.coarse_ctl = H["ctl"].data_ptr()
+        opts.coarse_opts = H["opts"]
+        self._slab_levels, self._slab_opts, self._coarse_H = levels, opts, H
+        self.native = True
+
+    def _launch_native(self):
+        rc = _lib.load().dgb_vcycle_slab(self.comm, self._slab_levels, len(self.grids), ctypes.byref(self._slab_opts),
+                                         self.ctl.data_ptr(), self.partials.data_ptr(), self.sumsq.data_ptr(), self._st())
+        _lib.check(rc, "dgb_vcycle_slab")
+
+    def _native_cycle(self):
+        """One V-cycle through dgb_vcycle_slab.  The launch sequence of a cycle is fixed (the smoother's early exit is
+        a device-side flag, the collectives count their sequence numbers on the device), so from the third call on it
+        is replayed as ONE CUDA graph: at 8 GPUs a rank's ~400 short launches per cycle are launch-bound otherwise."""
+        import torch
+        if self._graph is not None:
+            self._graph.replay()
+            self.graph_replays += 1
+            return
+        self._native_calls += 1
+        if self._native_calls < 3 or os.environ.get("DGB_MGPU_GRAPH", "1") == "0" or self._graph_failed:
+            self._launch_native()
+            return
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            L = _lib.load()
+            before = L.dgb_launch_count(0)
+            with torch.cuda.graph(g):
+                self._launch_native()
+            self.graph_launches = int(L.dgb_launch_count(0) - before)     # kernels one replay launches
+            self._graph = g
+        except Exception:                       # capture is an optimisation: fall back to plain launches
+            self._graph_failed = True
+            torch.cuda.synchronize()
+            self._launch_native()
+            return
+        self._graph.replay()
+        self.graph_replays += 1
+
+    def close(self):
+        self._graph = None
+        if getattr(self, "comm", None) is not None:
+            _lib.require_cuda().cuda.synchronize()
+            self.vec = [(rhs, None, r) for rhs, _, r in self.vec]      # views into the arena die with it
+            self._coarse_rhs = None
+            _lib.load().dgb_comm_destroy(self.comm)
+            self.comm = None
+            self.native = False
+
+    def check_native_error(self):
+        if getattr(self, "comm", None) is not None:
+            err = _lib.load().dgb_comm_error(self.comm, 1)
+            if err:
+                raise _lib.DgbError(f"a peer did not arrive at a collective within the time limit (dgb_comm_error={err})")
+            _lib.check_device_error([g.d_mailbox for g in self.grids])
 
     # ---- building blocks -------------------------------------------------------------------
     def _st(self):
@@ -204,6 +371,15 @@ class DistributedSolver:
         first_direction != 0: this is the entry residual of a lexicographic smoother call whose first pass runs in
         that direction -- it shares the launch of that pass's dependency-free part; returns True when it did."""
         import torch.distributed as dist
+        if getattr(self, "native", False) and u.data_ptr() == self.vec[k][1].data_ptr() and first_direction == 0:
+            g = self.grids[k]
+            L = _lib.load()
+            _lib.check(L.dgb_halo_exchange(self.comm, self._slab_levels[k].u_block, g.Ni * g.b,
+                                           g.Nj - g.ghost_lo - g.ghost_hi, self._st()), "dgb_halo_exchange")
+            _lib.call("dgb_bsr_residual", self.ops[k], rhs, u, r, self.partials, self.sumsq, skip, self._st())
+            _lib.check(L.dgb_allreduce_sum(self.comm, self.sumsq.data_ptr(), 0, None, 0, self._st()), "dgb_allreduce_sum")
+            self._entry_fused = False
+            return self.sumsq
         self._halo(k, u)
         fused = False
         if first_direction != 0 and skip is None:
@@ -303,6 +479,9 @@ class DistributedSolver:
     def vcycle(self, k=None):
         """One V-cycle on distributed level k (default: finest).  vec[k] = (rhs, u, r)."""
         import torch.distributed as dist
+        if getattr(self, "native", False) and (k is None or k == len(self.grids) - 1):
+            self._native_cycle()
+            return
         k = len(self.grids) - 1 if k is None else k
         g, st = self.grids[k], self._st()
         rhs, u, r = self.vec[k]
@@ -360,7 +539,24 @@ class DistributedSolver:
         return hist
 
 
-def build_distributed(settings, xn, yn, world, rank, min_rows=8, group=None, gs_mode=None):
+def native_transport_possible(group=None):
+    """One GPU per rank (kernels of different ranks wait for each other: they must not share a device) and a
+    device-capable process group."""
+    import torch
+    import torch.distributed as dist
+    if os.environ.get("DGB_MGPU_NATIVE", "1") == "0" or os.environ.get("DGB_MGPU_ONE_DEVICE") == "1":
+        return False
+    if not dist.is_initialized() or _host_staged(group):
+        return False
+    world = dist.get_world_size(group)
+    dev = torch.tensor([torch.cuda.current_device()], device="cuda")
+    devs = [torch.empty_like(dev) for _ in range(world)]
+    dist.all_gather(devs, dev, group=group)
+    ids = [int(d.item()) for d in devs]
+    return len(set(ids)) == world and torch.cuda.device_count() >= world
+
+
+def build_distributed(settings, xn, yn, world, rank, min_rows=8, group=None, gs_mode=None, native=None):
     """Build this rank's slab hierarchy (+ the gathered coarse hierarchy on rank 0).
     xn, yn: the FULL grid's nodes in Plot3D file order (every rank reads / generates them)."""
     from .dgfem import DGFEM, _int_list
@@ -402,8 +598,11 @@ def build_distributed(settings, xn, yn, world, rank, min_rows=8, group=None, gs_
     for g in grids:
         ds.problem.assemble(g)
         g.release_geometry()
+    mode = gs_mode or settings.get("solver.b200.gs_mode", "redblack")
+    if native is None:
+        native = world > 1 and mode in ("redblack", "slab_lexicographic") and native_transport_possible(group)
     coarse_solver = None
-    if rank == 0:
+    if rank == 0 or native:
         full_geo = Geometry(None, settings, nodes=(xn, yn))
         from .solver import Solver
         cgrids, cR, cP, ctypes_ = [], [], [], []
@@ -423,9 +622,11 @@ def build_distributed(settings, xn, yn, world, rank, min_rows=8, group=None, gs_
         coarse_solver.multigrid_type = ctypes_ if ctypes_ else ["geometric"]
         full_geo._dev = None
         torch.cuda.empty_cache()
-    mode = gs_mode or settings.get("solver.b200.gs_mode", "redblack")
-    return DistributedSolver(settings, grids, R_ops, P_ops, types, coarse_solver, part, gs_mode=mode,
-                             check_residual=settings.get("solver.b200.check_residual", True), group=group)
+    ds = DistributedSolver(settings, grids, R_ops, P_ops, types, coarse_solver, part, gs_mode=mode,
+                           check_residual=settings.get("solver.b200.check_residual", True), group=group)
+    if native:
+        ds.enable_native()
+    return ds
 
 
 def run_bench_multi_gpu(args, bench):
@@ -441,7 +642,10 @@ def run_bench_multi_gpu(args, bench):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, p = args.size, args.p
-    mode = args.gs_mode if args.gs_mode != "lexicographic" or args.exact_multi else "slab_lexicographic"
+    # N > 1 default: the 2-colour sweep (bandwidth-bound, the same iteration on any number of GPUs; pinned by the
+    # oracle's red_black_gauss_seidel).  The exact lexicographic order is a pipeline across slabs (--exact-multi),
+    # slab_lexicographic keeps the wavefront latency of Ni steps per pass on every rank.
+    mode = args.gs_mode if args.gs_mode != "lexicographic" or args.exact_multi else "redblack"
     settings = Settings(bench.make_params(n, p, mode, bool(args.check_residual)))
     settings.update_setting("solver.method", "multigrid")
     xn, yn = bench.rectangle_nodes_file_order(n, p)
@@ -461,6 +665,7 @@ def run_bench_multi_gpu(args, bench):
     torch.cuda.synchronize()
     L = _lib.load()
     L.dgb_launch_count(1)
+    replays0 = ds.graph_replays
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = bench.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -473,10 +678,13 @@ def run_bench_multi_gpu(args, bench):
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = torch.tensor([float(L.dgb_launch_count(0))], dtype=torch.float64, device="cuda")
+    # kernels launched inside the timed region: direct launches + what the graph replays launched
+    launches = torch.tensor([float(L.dgb_launch_count(0) + (ds.graph_replays - replays0) * ds.graph_launches)],
+                            dtype=torch.float64, device="cuda")
     dist.all_reduce(launches)
     clocks = sampler.stop() if sampler else None
     res = ds.residual_rms() / r0
+    ds.check_native_error()
     ms_per_step = float(ms.item()) / args.steps
     # end to end: host RHS/u chunks in, u chunk out, every step
     n_own = ds.n_owned[k]
@@ -503,6 +711,9 @@ def run_bench_multi_gpu(args, bench):
     if rank == 0:
         cfg = bench.workload_config(args)
         cfg["gs_mode"] = mode
+        cfg["transport"] = ("native: dgb_vcycle_slab, halo/all-reduce/all-gather kernels over peer memory (NVLink)" +
+                            (", one CUDA graph per cycle" if ds._graph is not None else "")) \
+            if ds.native else "torch.distributed (NCCL send/recv, all_reduce) sequenced from Python"
         cfg["partition"] = f"{world} slabs of {n // world} element rows, halo exchange per pass, levels with < 8 rows/rank gathered to rank 0"
         line = {"metric": "multigrid_vcycles_per_s", "value": 1e3 / ms_per_step, "unit": "V-cycles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -515,4 +726,6 @@ def run_bench_multi_gpu(args, bench):
                 "vcycle": {"normalised_residual_after_timed_cycles": res, "cycles_run": args.warmup + args.steps},
                 "vcycle_dof_per_s": n * n * (p + 1) ** 2 * 1e3 / ms_per_step, "setup_s": setup_s}
         print(json.dumps(line), flush=True)
+    ds.check_native_error()
+    ds.close()
     dist.destroy_process_group()

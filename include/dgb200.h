@@ -125,6 +125,12 @@ int dgb_bsr_apply(const dgb_operator *h_op, const double *x, double *y, void *st
 int dgb_bsr_residual(const dgb_operator *h_op, const double *rhs, const double *x, double *r,
                      double *partials, double *sumsq, const int32_t *skip, void *stream);
 
+/* The same right after a 2-colour pass that relaxed colour `relaxed` ((i + j + shift) & 1) last: those rows satisfy
+ * their equations -- their residual (rounding noise) is written as zero -- and only the rows of the other colour
+ * are evaluated: half the traffic of dgb_bsr_residual.  DG 5-point stencil only. */
+int dgb_bsr_residual_colour(const dgb_operator *h_op, const double *rhs, const double *x, double *r, int32_t relaxed,
+                            int32_t shift, double *partials, double *sumsq, const int32_t *skip, void *stream);
+
 /* sum(v^2) of a plain vector into *sumsq (device scalar). */
 int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream);
 
@@ -400,6 +406,73 @@ int dgb_assemble_rhs_stokes(const dgb_tables *t_uu, const dgb_tables *t_pu, cons
                             const double *f_mom, const double *f_cont, const double *g_u,
                             const double *g_p, int32_t Ni, int32_t Nj, double nu, double sigma,
                             double gamma, int32_t flags, double *rhs, void *stream);
+
+/* ---- multi-GPU: element slabs over peer memory (NVLink / NVSwitch) -------------------------------------
+ * The reference is a single process; these entry points carry its V-cycle across slabs of
+ * whole element rows, one process per GPU.  Every rank creates a communicator with an arena of the SAME size, the
+ * 64-byte export handles are exchanged out of band (any bootstrap: torch.distributed, MPI, a file) and every rank
+ * connects.  Allocation inside the arena is the caller's, with one rule: identical offsets on every rank.
+ * All collectives are stream-ordered kernel launches (no host synchronisation); the waits inside them are bounded
+ * (20 s) and report through dgb_comm_error (3 = a peer did not arrive).  Ranks must issue the same sequence of
+ * collectives.  One rank per device: kernels of different ranks wait for each other. */
+typedef struct dgb_comm dgb_comm;
+int dgb_comm_create(int32_t rank, int32_t world, int64_t arena_bytes, dgb_comm **out);
+int dgb_comm_handle_bytes(void);                          /* 64 */
+int dgb_comm_export(dgb_comm *c, void *h_handle);         /* h_handle: dgb_comm_handle_bytes() bytes          */
+int dgb_comm_connect(dgb_comm *c, const void *h_handles); /* world handles, rank order (own slot ignored)      */
+void *dgb_comm_arena(dgb_comm *c, int64_t *bytes);        /* device pointer of the arena's allocatable part    */
+int dgb_comm_error(dgb_comm *c, int32_t reset);           /* synchronises                                      */
+void dgb_comm_destroy(dgb_comm *c);
+
+/* Halo exchange of one vector.  `block` (in the arena, same offset on every rank) holds rows + 2 element rows of
+ * row_doubles doubles: [ghost row below | rows owned rows | ghost row above]; after the call the ghost rows hold the
+ * neighbour slabs' edge rows (rank - 1's last, rank + 1's first owned row).  Replaces nothing in the reference: it is
+ * what makes  grid.BSR @ u  (dgfem/solver.py:150, relaxation.py:202,208) and the smoother passes see the neighbour
+ * slab. */
+int dgb_halo_exchange(dgb_comm *c, double *block, int64_t row_doubles, int32_t rows, void *stream);
+
+/* *value (device scalar) <- sum over ranks, added in rank order on every rank (identical bits everywhere).
+ * mode 0: only that; 1: then dgb_smoother_begin(ctl, value, n_global); 2: then dgb_smoother_check(...). */
+int dgb_allreduce_sum(dgb_comm *c, double *value, int32_t mode, dgb_smoother_ctl *ctl, int64_t n_global, void *stream);
+
+/* dst_block (in the arena, same offset everywhere, world*chunk doubles) <- [src of rank 0 | src of rank 1 | ...]
+ * on every rank ("coarsest level gathered", north_star; here every rank holds the gathered level). */
+int dgb_allgather(dgb_comm *c, const double *src, double *dst_block, int64_t chunk, void *stream);
+
+/* One level of a slab hierarchy: `lev` as in dgb_vcycle (op carries the DGB_FLAG_GHOST_* bits, Nj counts the ghost
+ * rows; lev.R / lev.P / transfer_kind link this level, as the coarse side, to the next finer slab level);
+ * lev.u must be u_block + (1 - ghost_lo) * Ni * b. */
+typedef struct dgb_slab_level {
+    dgb_level lev;
+    double *u_block;           /* [rows + 2][Ni * b] in the arena                                   */
+    int32_t ghost_lo, ghost_hi;
+    int32_t colour_shift;      /* (global row of local row 0) & 1: all ranks colour the global grid   */
+    int32_t pad;
+    int64_t n_global;          /* scalar unknowns of the level over all ranks (residual norms)        */
+} dgb_slab_level;
+
+#define DGB_GS_SLAB_LEXICOGRAPHIC 2   /* lexicographic inside a slab, neighbour rows as before the pass */
+
+typedef struct dgb_slab_opts {
+    int32_t gs_mode;           /* DGB_GS_REDBLACK | DGB_GS_SLAB_LEXICOGRAPHIC                          */
+    int32_t check_residual;
+    /* link between the coarsest slab level (fine side) and the finest replicated level (coarse side) */
+    int32_t link_kind, link_nc, link_nf;
+    int32_t link_Ni_c, link_rows_c;   /* this rank's un-ghosted chunk of that coarse level             */
+    int32_t n_coarse;
+    const double *link_R, *link_P;
+    double *link_rhs_local;    /* [link_rows_c * link_Ni_c * link_nc] scratch                          */
+    /* the replicated hierarchy below (every rank runs it on the gathered level: identical bits);
+     * coarse_levels[n_coarse - 1].rhs is the all-gather destination and must lie in the arena */
+    const dgb_level *coarse_levels;
+    dgb_smoother_ctl *coarse_ctl;
+    dgb_vcycle_opts coarse_opts;
+} dgb_slab_opts;
+
+/* One V-cycle on the finest slab level (levels[nlevels - 1]): Solver.multigrid_V_cycle (dgfem/solver.py:141-207)
+ * with the smoother of dgfem/relaxation.py:198-218 across slabs.  ctl: nlevels control blocks. */
+int dgb_vcycle_slab(dgb_comm *comm, const dgb_slab_level *h_levels, int32_t nlevels, const dgb_slab_opts *h_opts,
+                    dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream);
 
 /* ---- post-processing --------------------------------------------------------------------------
  * replaces the per-element loop of DGFEM.solve (dgfem/dgfem.py:188-232): u_nodal[e] = V_DOF_grid @ u_e at the

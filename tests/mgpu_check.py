@@ -40,7 +40,9 @@ def main():
         s = Settings(bench.make_params(n, 2, mode, True))
         s.update_setting("solver.method", "multigrid")
         ds = build_distributed(s, xn, yn, world, rank, gs_mode=mode)
+        transport = "native (peer memory, dgb_vcycle_slab)" if ds.native else "torch.distributed"
         hist = np.array(ds.solve(tol=1e-6, max_cycles=60))
+        ds.check_native_error()
         ref = None
         if rank == 0 and single_mode is not None:
             s1 = Settings(bench.make_params(n, 2, single_mode, True))
@@ -48,7 +50,7 @@ def main():
             d.solver.solve()
             ref = np.array(d.solver.residuals)
         if rank == 0:
-            msg = f"[mgpu_check] world={world} n={n} mode={mode}: {len(hist) - 1} cycles, final {hist[-1]:.3e}"
+            msg = f"[mgpu_check] world={world} n={n} mode={mode} [{transport}]: {len(hist) - 1} cycles, final {hist[-1]:.3e}"
         if rank == 0 and single_mode is None:
             # the oracle's slab iteration on the same grid (CPU; the reference's assembly restated in NumPy)
             from dgoracle import multigrid, plot3d
@@ -62,6 +64,7 @@ def main():
                        f"{np.max(np.abs(hist[:len(ref)] - ref[:len(hist)]) / ref[:len(hist)]):.2e} -> {'OK' if same else 'MISMATCH'}"
                 ok &= bool(same)
             print(msg, flush=True)
+        ds.close()
         del ds
         torch.cuda.empty_cache()
     flag = torch.tensor([1.0 if ok else 0.0], device="cpu" if dist.get_backend() == "gloo" else "cuda")
