@@ -649,6 +649,8 @@ def main():
                     help="c3 = the V-cycle workload (BASELINE configs[2], default); c4 / c5 = configs[3] / configs[4]")
     ap.add_argument("--p5-apply", type=int, default=1,
                     help="also measure the p=5 operator apply (configs[3]'s operator, 1024^2) in the default run")
+    ap.add_argument("--min-rows", type=int, default=0,
+                    help="N>1: levels with fewer element rows per rank are replicated (0 = the library's default)")
     ap.add_argument("--exact-multi", action="store_true",
                     help="N>1: keep the exact global lexicographic order (slabs sweep one after the other)")
     args = ap.parse_args()

@@ -49,6 +49,13 @@ class SlabPartition:
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
 
 
+def default_min_rows(world):
+    """Levels with fewer element rows per rank than this are replicated instead of distributed (measured on 8 B200,
+    profiles/r02_bench_2048_n8_min_rows.md: a distributed level costs ~36 collectives of a few microseconds per
+    cycle whatever its size, a replicated 128^2 level less than that)."""
+    return 64
+
+
 def distributed_levels(Nj, world, h_factors, min_rows=8):
     """Which h-coarsening factors stay distributed: every distributed level needs >= min_rows rows per
     rank and an even row count per rank on the next finer level (2x2 children stay inside a slab)."""
@@ -600,7 +607,9 @@ def build_distributed(settings, xn, yn, world, rank, min_rows=8, group=None, gs_
         g.release_geometry()
     mode = gs_mode or settings.get("solver.b200.gs_mode", "redblack")
     if native is None:
-        native = world > 1 and mode in ("redblack", "slab_lexicographic") and native_transport_possible(group)
+        # one rank: the same C++ driver and collective kernels with nobody to wait for (what a 1-GPU box can test)
+        native = mode in ("redblack", "slab_lexicographic") and os.environ.get("DGB_MGPU_NATIVE", "1") != "0" and \
+            (world == 1 or native_transport_possible(group))
     coarse_solver = None
     if rank == 0 or native:
         full_geo = Geometry(None, settings, nodes=(xn, yn))
@@ -650,7 +659,8 @@ def run_bench_multi_gpu(args, bench):
     settings.update_setting("solver.method", "multigrid")
     xn, yn = bench.rectangle_nodes_file_order(n, p)
     t0 = time.perf_counter()
-    ds = build_distributed(settings, xn, yn, world, rank, gs_mode=mode)
+    mr = getattr(args, "min_rows", 0) or default_min_rows(world)
+    ds = build_distributed(settings, xn, yn, world, rank, min_rows=mr, gs_mode=mode)
     del xn, yn
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
@@ -714,7 +724,8 @@ def run_bench_multi_gpu(args, bench):
         cfg["transport"] = ("native: dgb_vcycle_slab, halo/all-reduce/all-gather kernels over peer memory (NVLink)" +
                             (", one CUDA graph per cycle" if ds._graph is not None else "")) \
             if ds.native else "torch.distributed (NCCL send/recv, all_reduce) sequenced from Python"
-        cfg["partition"] = f"{world} slabs of {n // world} element rows, halo exchange per pass, levels with < 8 rows/rank gathered to rank 0"
+        cfg["partition"] = (f"{world} slabs of {n // world} element rows, halo exchange per pass, levels with < {mr} "
+                            f"rows/rank {'replicated on every rank (all-gather)' if ds.native else 'gathered to rank 0'}")
         line = {"metric": "multigrid_vcycles_per_s", "value": 1e3 / ms_per_step, "unit": "V-cycles/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
