@@ -522,3 +522,31 @@ def test_direct_solve_and_export():
     assert abs(d.L2_error_u - np.sqrt((delta ** 2).mean())) < 1e-13
     vts = d.solution_visualization_filepath + ".vts"
     assert os.path.exists(vts) and os.path.getsize(vts) > fine.Ni * fine.Nj * N1 * N1 * 8 * 6
+
+
+def test_midsize_vcycle_against_oracle():
+    """256 x 256, p=2 (590 k DOFs, levels p 2,1 + h 2..64): the largest case the oracle finishes in seconds.  Operator
+    apply (a16), one symmetric smoother call with its residual tests (a14) and one V-cycle (a13) against the oracle
+    on the same inputs -- the bench compares the 512^2 V-cycle the same way (bench.py `parity`)."""
+    import bench
+    from dgoracle import multigrid, plot3d, relax
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.relaxation import Relaxation, bsr_apply
+    from dg_multigrid_solver_b200.settings import Settings
+    n, p = 256, 2
+    s = Settings(bench.make_params(n, p, "lexicographic", True))
+    d = DGFEM(settings=s, geometry=Geometry(None, s, nodes=bench.rectangle_nodes_file_order(n, p)), solve_multigrid=True,
+              write_results=False)
+    x, y = plot3d.rectangle_nodes(n, n, p)
+    H = multigrid.Hierarchy(x, y, p, [1, p], bench.h_factors(n), exact_u=bench.MMS_U, rhs_all_levels=False)
+    fine, fo = d.grids[-1], H.levels[-1]
+    assert np.array_equal(fine.BSR.indices, fo.A.indices)
+    assert rel_err(fine.RHS, fo.RHS) < 1e-12
+    u0 = np.sin(0.37 * np.arange(fo.RHS.size)) * 0.1
+    assert rel_err(bsr_apply(fine, u0), fo.A @ u0) < 1e-12
+    u_s = Relaxation.block_gauss_seidel_pyamg(grid=fine, RHS=fine.RHS, u=u0, direction="symmetric", max_iterations=2)
+    assert rel_err(u_s, relax.block_gauss_seidel_pyamg(fo.A, fo.RHS, u0, "symmetric", 1, 2)) < 1e-11
+    u1 = d.solver.multigrid_V_cycle(k=len(d.grids), RHS=fine.RHS, u=np.zeros_like(fine.RHS))
+    uo = multigrid.v_cycle(H, multigrid.Schedule(), len(H.levels), fo.RHS, np.zeros_like(fo.RHS))
+    assert rel_err(u1, uo) < 1e-10
