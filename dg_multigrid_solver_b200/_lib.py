@@ -30,7 +30,8 @@ class Operator(ctypes.Structure):
     _fields_ = [("Ni", c_i32), ("Nj", c_i32), ("b", c_i32), ("nnzb", c_i32),
                 ("stencil", c_i32), ("reserved", c_i32),
                 ("data", c_vp), ("indices", c_vp), ("indptr", c_vp), ("dinv", c_vp), ("gs_data", c_vp),
-                ("gs_mailbox", c_vp), ("gs_chain", c_vp)]
+                ("gs_mailbox", c_vp), ("gs_chain", c_vp),
+                ("gs_rows", c_vp), ("h_gs_offsets", c_vp), ("gs_nlevels_fwd", c_i32), ("gs_nlevels_bwd", c_i32)]
 
 
 class Level(ctypes.Structure):
@@ -104,6 +105,7 @@ SIGNATURES = {
     "dgb_bsr_apply": (c_i32, [OP, c_vp, c_vp, c_vp]),
     "dgb_bsr_residual": (c_i32, [OP, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_bsr_residual_colour": (c_i32, [OP, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "dgb_bsr_spgemm": (c_i32, [c_i32, c_i32] + [c_vp] * 10),
     "dgb_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dgb_block_diag_inverse": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_build_gs_stream": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),

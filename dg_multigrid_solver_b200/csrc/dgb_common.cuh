@@ -64,6 +64,25 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         return 2;                                                                       \
     }
 
+// The row-per-thread kernels (apply / residual / relaxation / block inverse) also exist for the block sizes SciPy's
+// blocksize heuristic picks for the global-order Stokes blocks (2, 3, 6).
+#define DGB_DISPATCH_B_ANY(b, ...)                                                      \
+    switch (b) {                                                                        \
+    case 1: { constexpr int B = 1; __VA_ARGS__; } break;                                \
+    case 2: { constexpr int B = 2; __VA_ARGS__; } break;                                \
+    case 3: { constexpr int B = 3; __VA_ARGS__; } break;                                \
+    case 4: { constexpr int B = 4; __VA_ARGS__; } break;                                \
+    case 6: { constexpr int B = 6; __VA_ARGS__; } break;                                \
+    case 9: { constexpr int B = 9; __VA_ARGS__; } break;                                \
+    case 16: { constexpr int B = 16; __VA_ARGS__; } break;                              \
+    case 22: { constexpr int B = 22; __VA_ARGS__; } break;                              \
+    case 25: { constexpr int B = 25; __VA_ARGS__; } break;                              \
+    case 36: { constexpr int B = 36; __VA_ARGS__; } break;                              \
+    default:                                                                            \
+        dgb::set_error("unsupported block size b=%d", (int)(b));                        \
+        return 2;                                                                       \
+    }
+
 // sum_c a[c] * x[c], c = 0..B-1 in order (scipy's bsr_matvec accumulation order), with the matrix row read in
 // aligned 16-byte pieces.  Rows of an odd-b block start at 8 (mod 16) every other row: the aligned window then
 // begins one double early / ends one double late, and the stray entry meets a zero factor.  (A warp of these row

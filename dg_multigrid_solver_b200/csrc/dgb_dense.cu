@@ -114,6 +114,38 @@ k_dense_matvec(const double *__restrict__ M, int n, const double *__restrict__ r
     if (lane == 0) u[row] = acc;
 }
 
+// C = A B on C's given block structure: one thread per scalar entry of C; blocks of A's row in stored order
+__global__ void __launch_bounds__(256)
+k_bsr_spgemm(int b, int n_brow, const int32_t *__restrict__ a_indptr, const int32_t *__restrict__ a_indices,
+             const double *__restrict__ a_data, const int32_t *__restrict__ b_indptr,
+             const int32_t *__restrict__ b_indices, const double *__restrict__ b_data,
+             const int32_t *__restrict__ c_indptr, const int32_t *__restrict__ c_indices, double *__restrict__ c_data) {
+    const int bb = b * b;
+    const long long total = (long long)c_indptr[n_brow] * bb;
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+        const int jj = (int)(t / bb);
+        const int rc = (int)(t - (long long)jj * bb);
+        const int r = rc / b, c = rc - r * b;
+        int lo = 0, hi = n_brow;                       // block row of stored block jj of C
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (c_indptr[mid] <= jj) lo = mid; else hi = mid;
+        }
+        const int I = lo, J = c_indices[jj];
+        double acc = 0.0;
+        for (int ka = a_indptr[I]; ka < a_indptr[I + 1]; ++ka) {
+            const int K = a_indices[ka];
+            for (int kb = b_indptr[K]; kb < b_indptr[K + 1]; ++kb) {
+                if (b_indices[kb] != J) continue;
+                const double *ar = a_data + (size_t)ka * bb + (size_t)r * b;
+                const double *bc = b_data + (size_t)kb * bb + c;
+                for (int m = 0; m < b; ++m) acc = fma(ar[m], bc[(size_t)m * b], acc);
+            }
+        }
+        c_data[t] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fill_sentinel(double *v, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
         v[i] = __longlong_as_double(-1LL);
@@ -152,6 +184,17 @@ int dgb_dense_inverse(const double *data, const int32_t *indices, const int32_t 
 int dgb_dense_solve(const double *inverse, int32_t n, const double *rhs, double *u, void *stream) {
     DGB_ARG(inverse && rhs && u && n > 0 && rhs != u);
     k_dense_matvec<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(inverse, n, rhs, u);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+int dgb_bsr_spgemm(int32_t b, int32_t n_brow, const int32_t *a_indptr, const int32_t *a_indices, const double *a_data,
+                   const int32_t *b_indptr, const int32_t *b_indices, const double *b_data, const int32_t *c_indptr,
+                   const int32_t *c_indices, double *c_data, void *stream) {
+    DGB_ARG(b > 0 && n_brow > 0 && a_indptr && a_indices && a_data && b_indptr && b_indices && b_data && c_indptr &&
+            c_indices && c_data);
+    k_bsr_spgemm<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(b, n_brow, a_indptr, a_indices, a_data, b_indptr,
+                                                                    b_indices, b_data, c_indptr, c_indices, c_data);
     DGB_LAUNCH_OK();
     return 0;
 }

@@ -40,6 +40,7 @@ struct Sel {
     int Ni, Nj;
     int i_lo;   // mode 2: first i on the diagonal
     int count;  // number of candidate items (mode 0/1: Ni*Nj, mode 2: elements on the diagonal)
+    const int32_t *list;   // mode 4: explicit block-row list (one dependency level of a generic Gauss-Seidel pass)
 };
 
 __device__ __forceinline__ int sel_element(const Sel &s, int idx) {
@@ -48,6 +49,7 @@ __device__ __forceinline__ int sel_element(const Sel &s, int idx) {
         const int i = idx % s.Ni, j = idx / s.Ni;
         return (((i + j + s.i_lo) & 1) == s.sel) ? idx : -1;
     }
+    if (s.mode == 4) return s.list[idx];
     if (s.mode == 3) {     // item = (row j, pair m): the element of the pair with (i + j + shift) & 1 == sel
         const int np = (s.Ni + 1) >> 1;
         const int j = idx / np, m = idx - j * np;
@@ -551,8 +553,8 @@ int dgb_bsr_apply(const dgb_operator *op, const double *x, double *y, void *stre
     DGB_ARG(x && y);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
-    Sel sel{0, 0, N, 1, 0, N};
-    DGB_DISPATCH_B(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_APPLY>()), RowCfg<B>::NT, 0, st>>>(
+    Sel sel{0, 0, N, 1, 0, N, nullptr};
+    DGB_DISPATCH_B_ANY(op->b, k_rows<B, MODE_APPLY><<<rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_APPLY>()), RowCfg<B>::NT, 0, st>>>(
                               op->data, op->indices, op->indptr, nullptr, nullptr, x, y, nullptr, 1.0, sel, nullptr));
     DGB_LAUNCH_OK();
     return 0;
@@ -566,8 +568,8 @@ int dgb_bsr_residual(const dgb_operator *op, const double *rhs, const double *x,
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     int grid = 1;
-    Sel sel{0, 0, N, 1, 0, N};
-    DGB_DISPATCH_B(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
+    Sel sel{0, 0, N, 1, 0, N, nullptr};
+    DGB_DISPATCH_B_ANY(op->b, grid = rows_grid(N, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
                    k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
                        op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
     DGB_LAUNCH_OK();
@@ -586,8 +588,8 @@ int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const dou
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     int grid = 1;
-    Sel sel{3, 1 - relaxed, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj};
-    DGB_DISPATCH_B(op->b, grid = rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
+    Sel sel{3, 1 - relaxed, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj, nullptr};
+    DGB_DISPATCH_B_ANY(op->b, grid = rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
                    k_rows<B, MODE_RESIDUAL><<<grid, RowCfg<B>::NT, 0, st>>>(
                        op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
     DGB_LAUNCH_OK();
@@ -613,7 +615,7 @@ int dgb_block_diag_inverse(const double *data, const int32_t *indices, const int
     DGB_ARG(data && indices && indptr && dinv && info && n_brow > 0);
     cudaStream_t st = (cudaStream_t)stream;
     DGB_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    DGB_DISPATCH_B(b, k_block_diag_inverse<B><<<(n_brow + 3) / 4, 128, 0, st>>>(data, indices, indptr,
+    DGB_DISPATCH_B_ANY(b, k_block_diag_inverse<B><<<(n_brow + 3) / 4, 128, 0, st>>>(data, indices, indptr,
                                                                               n_brow, dinv, info));
     DGB_LAUNCH_OK();
     return 0;
@@ -625,7 +627,7 @@ int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_
     DGB_ARG(data && indices && indptr && dinv && gs_data && n_brow > 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (int)(((size_t)n_brow * 32 + 255) / 256);
-    DGB_DISPATCH_B(b, k_build_gs_stream<B><<<grid, 256, 0, st>>>(data, indices, indptr, dinv, n_brow,
+    DGB_DISPATCH_B_ANY(b, k_build_gs_stream<B><<<grid, 256, 0, st>>>(data, indices, indptr, dinv, n_brow,
                                                                 gs_data));
     DGB_LAUNCH_OK();
     return 0;
@@ -635,7 +637,7 @@ int dgb_build_gs_stream(const double *data, const int32_t *indices, const int32_
 static int relax_launch(const dgb_operator *op, const double *rhs, const double *x_in, double *x_out,
                         double omega, Sel sel, const int32_t *skip, cudaStream_t st) {
     if (sel.count <= 0) return 0;
-    DGB_DISPATCH_B(op->b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RELAX>()), RowCfg<B>::NT, 0, st>>>(
+    DGB_DISPATCH_B_ANY(op->b, k_rows<B, MODE_RELAX><<<rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RELAX>()), RowCfg<B>::NT, 0, st>>>(
                               op->data, op->indices, op->indptr, op->dinv, rhs, x_in, x_out, nullptr, omega, sel, skip));
     DGB_LAUNCH_OK();
     return 0;
@@ -649,7 +651,24 @@ static int wavefront_pass(const dgb_operator *op, const double *rhs, double *x, 
         const int c = direction > 0 ? k : ndiag - 1 - k;
         const int i_lo = c - (Nj - 1) > 0 ? c - (Nj - 1) : 0;
         const int i_hi = c < Ni - 1 ? c : Ni - 1;
-        Sel sel{2, c, Ni, Nj, i_lo, i_hi - i_lo + 1};
+        Sel sel{2, c, Ni, Nj, i_lo, i_hi - i_lo + 1, nullptr};
+        int rc = relax_launch(op, rhs, x, x, omega, sel, skip, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// Arbitrary (structurally symmetric) BSR: the rows of one dependency level of the lexicographic sweep have no
+// coupling among themselves, so a level is one relaxation launch over its row list (schedule built by the caller,
+// dgb_operator.gs_rows / h_gs_offsets); the levels run in order.  Exactly pyamg's sequential sweep.
+static int level_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
+                      const int32_t *skip, cudaStream_t st) {
+    const int N = op->Ni * op->Nj;
+    const int nl = direction > 0 ? op->gs_nlevels_fwd : op->gs_nlevels_bwd;
+    const int32_t *off = op->h_gs_offsets + (direction > 0 ? 0 : op->gs_nlevels_fwd + 1);
+    const int32_t *rows = op->gs_rows + (direction > 0 ? 0 : N);
+    for (int l = 0; l < nl; ++l) {
+        Sel sel{4, 0, N, 1, 0, off[l + 1] - off[l], rows + off[l]};
         int rc = relax_launch(op, rhs, x, x, omega, sel, skip, st);
         if (rc) return rc;
     }
@@ -666,6 +685,13 @@ static int lexicographic_pass(const dgb_operator *op, const double *rhs, double 
     if (use_stream(op) && op->gs_data != nullptr && op->gs_mailbox != nullptr)
         return gs_rows_launch(op->b, op->gs_data, rhs, x, op->gs_mailbox, op->Ni, op->Nj, op->stencil, direction,
                               omega, skip, st);
+    if (op->stencil < 0) {
+        if (op->gs_rows == nullptr || op->h_gs_offsets == nullptr) {
+            set_error("lexicographic Gauss-Seidel on an arbitrary BSR matrix needs a level schedule (dgb_operator.gs_rows)");
+            return 3;
+        }
+        return level_pass(op, rhs, x, omega, direction, skip, st);
+    }
     return wavefront_pass(op, rhs, x, omega, direction, skip, st);
 }
 
@@ -680,7 +706,7 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
-            Sel sel{3, colour, op->Ni, op->Nj, 0, ((op->Ni + 1) / 2) * op->Nj};
+            Sel sel{3, colour, op->Ni, op->Nj, 0, ((op->Ni + 1) / 2) * op->Nj, nullptr};
             rc = relax_launch(op, rhs, x, x, 1.0, sel, skip, st);
             if (rc) return rc;
         }
@@ -738,7 +764,7 @@ int dgb_block_gs_colour(const dgb_operator *op, const double *rhs, double *x, in
     int rc = check_op(op);
     if (rc) return rc;
     DGB_ARG(op->dinv && rhs && x && (colour == 0 || colour == 1));
-    Sel sel{3, colour, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj};
+    Sel sel{3, colour, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj, nullptr};
     return relax_launch(op, rhs, x, x, 1.0, sel, skip, (cudaStream_t)stream);
 }
 
@@ -750,7 +776,7 @@ int dgb_block_relax_sweep(const dgb_operator *op, const double *rhs, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     const int N = op->Ni * op->Nj;
     if (x_in == x_out) return lexicographic_pass(op, rhs, x_out, omega, +1, nullptr, st);
-    Sel sel{0, 0, op->Ni, op->Nj, 0, N};
+    Sel sel{0, 0, op->Ni, op->Nj, 0, N, nullptr};
     return relax_launch(op, rhs, x_in, x_out, omega, sel, nullptr, st);
 }
 

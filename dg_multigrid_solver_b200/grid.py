@@ -194,6 +194,8 @@ class Grid:
     @property
     def BSR(self):
         """scipy.sparse.bsr_array copy of the device operator (discrete_system.py:145)."""
+        if self._BSR is None and getattr(self, "ordering", "local") == "global":
+            self._BSR = self.BSR_global.to_scipy()          # Stokes global ordering (discrete_system.py:745)
         if self._BSR is None and self.d_data is not None:
             import scipy.sparse as sp
             n = self.N * self.N_DOF_sol_tot

@@ -146,12 +146,96 @@ class Relaxation:
             return d_u.cpu().numpy()
         return d_u
 
+    @classmethod
+    def _bgs_block(cls, blk, d_rhs, sweeps):
+        """Relaxation.block_gauss_seidel_pyamg(grid, rhs, u=0, direction='symmetric', max_iterations=sweeps) with
+        grid.BSR = one global-order block (dgfem/relaxation.py:252,256,263): the level-scheduled lexicographic
+        sweep of the generic kernels, block size = the block's (SciPy-chosen) blocksize."""
+        torch = _lib.require_cuda()
+        ws = _Workspace.get()
+        blk.prepare_gauss_seidel()
+        x = torch.zeros(blk.shape[0], dtype=torch.float64, device="cuda")
+        ws.ctl.zero_()
+        _lib.call("dgb_block_gauss_seidel_pyamg", blk.operator(), d_rhs, x, 0, int(sweeps), _lib.GS_LEXICOGRAPHIC, 1,
+                  ws.ctl, ws.partials, ws.sumsq, _lib.stream_ptr())
+        return x
+
+    @classmethod
+    def distributive_gauss_seidel(cls, grid, RHS, u=None, inner_smoother="block_gauss_seidel_pyamg",
+                                  splitting="classical_exact", omega=1, max_iterations=1e3, settings=None):
+        """dgfem/relaxation.py:221-283, `lsq` splitting (the one Solver.solve_smoother uses, solver.py:63): per outer
+        iteration three symmetric block-GS iterations (on A, on D G, on D G) and eight block mat-vecs, all on the
+        device; one scalar per outer iteration comes back for the reference's convergence test."""
+        import os
+        import pickle
+        torch = _lib.require_cuda()
+        if settings.problem.type != "Stokes":
+            raise ValueError("Distributive Gauss-Seidel is only possible for the Stokes equations")
+        if settings.solution.ordering != "global":
+            raise ValueError("The solution ordering must be global in order to use distributive Gauss-Seidel")
+        if splitting != "lsq":
+            raise NotImplementedError(f"distributive_gauss_seidel splitting '{splitting}' is outside the accelerated "
+                                      "path (the reference's -s run uses 'lsq', dgfem/solver.py:63)")
+        from .stokes import Stokes
+        A, D, G = grid.BSR_block_A, grid.BSR_block_D, grid.BSR_block_G
+        DG = Stokes(settings).block_DG(grid)
+        d_rhs, host = _to_device(RHS)
+        if isinstance(u, np.ndarray):
+            d_u = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64)).cuda()
+        elif u is None or not hasattr(u, "data_ptr"):
+            d_u = torch.zeros_like(d_rhs)
+        else:
+            d_u = u.clone()
+        n_u = A.shape[0]
+        f_mom, f_cont = d_rhs[:n_u], d_rhs[n_u:]
+
+        def full_residual_rms(v):
+            r1 = f_mom - A.apply(v[:n_u]) - G.apply(v[n_u:])
+            r2 = f_cont - D.apply(v[:n_u])
+            return float(torch.sqrt(((r1 * r1).sum() + (r2 * r2).sum()) / d_rhs.numel()).item())
+        residual_0 = full_residual_rms(d_u)
+        residuals = []
+        sweeps, n = 1, 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            while n < max_iterations:
+                u_k, p_k = d_u[:n_u], d_u[n_u:]
+                rhs_mom = f_mom - A.apply(u_k) - G.apply(p_k)
+                du_star = cls._bgs_block(A, rhs_mom, sweeps)
+                rhs_cont = f_cont - D.apply(u_k + du_star)
+                dp_star = cls._bgs_block(DG, rhs_cont, sweeps)
+                du = du_star + G.apply(dp_star)
+                rhs_dg = -D.apply(A.apply(G.apply(dp_star)))
+                dp = cls._bgs_block(DG, rhs_dg, sweeps)
+                d_u[:n_u] += du
+                d_u[n_u:] += dp
+                residual = np.float64(full_residual_rms(d_u)) / np.float64(residual_0)
+                residuals.append(float(residual))
+                if residual < 1e-6:
+                    print(f"Residual reduced by 6 orders in {n} sweeps")         # relaxation.py:272
+                    break
+                elif residual > 1e10:
+                    print(f"diverging, residual={residual:.6e}")
+                    raise SystemExit()
+                n += 1
+        _lib.check_device_error([])
+        cls.last_residuals = residuals
+        try:                                                                       # relaxation.py:229-234,282-283
+            path = os.path.join(os.getcwd(), "postprocessing", "pickles", "relaxation")
+            os.makedirs(path, exist_ok=True)
+            name = f"residuals_{settings.problem.type}_{grid.Ni}X{grid.Nj}_nPoly{grid.P_grid}_Pu{grid.P_sol.get('u')}" \
+                   f"_Pp{grid.P_sol.get('p')}_{splitting}" + ("_circle" if settings.grid.circular else "_rectangle") + ".pkl"
+            with open(os.path.join(path, name), "wb") as f:
+                pickle.dump(residuals, f)
+        except OSError:
+            pass
+        return d_u.cpu().numpy() if host else d_u
+
     # names the reference resolves but that are outside the accelerated path (SURVEY.md section 2.1 row 8)
     @classmethod
     def _out_of_scope(cls, *a, **k):
         raise NotImplementedError("this smoother is outside the B200 hot path (SURVEY.md section 2.1 row 8)")
 
-    jacobi = jacobi_pyamg = gauss_seidel = gauss_seidel_pyamg = distributive_gauss_seidel = _out_of_scope
+    jacobi = jacobi_pyamg = gauss_seidel = gauss_seidel_pyamg = _out_of_scope
     calculate_amplification = _out_of_scope
 
 

@@ -61,6 +61,9 @@ class Solver:
     def solve_smoother(self, grid, RHS):
         """dgfem/solver.py:61-66."""
         name = self.settings.solver.smoother
+        if name == "distributive_gauss_seidel":                                   # dgfem/solver.py:62-63
+            return Relaxation.distributive_gauss_seidel(grid, RHS, max_iterations=1000000, splitting="lsq",
+                                                        settings=self.settings)
         return getattr(Relaxation, name)(grid, RHS, max_iterations=100, direction="symmetric")
 
     # ------------------------------------------------------------------------------------
@@ -145,6 +148,8 @@ class Solver:
     def coarse_direct_inverse(grid):
         """Dense inverse of a level's operator (dgb_dense_inverse): the device-side `solve_directly`."""
         torch = _lib.require_cuda()
+        if getattr(grid, "ordering", "local") == "global":       # Stokes, global ordering: the regrouped matrix
+            grid = grid.BSR_global
         b = grid.d_data.shape[1]
         N = grid.d_indptr.numel() - 1
         inv = torch.empty((N * b, N * b), dtype=torch.float64, device="cuda")

@@ -87,6 +87,13 @@ typedef struct dgb_operator {
                                 every 8 bytes 0xFF (all-ones NaN) outside a pass, or NULL   */
     double *gs_chain;        /* [dgb_gs_chain_len()] record stream of the chained lexicographic GS
                                 kernel (dgb_build_gs_chain), or NULL                        */
+    /* stencil == -1 only: level schedule of the lexicographic sweep on an arbitrary, structurally symmetric BSR
+     * matrix (the global-order Stokes blocks).  gs_rows (device): the N block rows grouped by forward dependency
+     * level, then the N rows grouped by backward level; h_gs_offsets (HOST): fwd offsets [nlevels_fwd + 1], then
+     * bwd offsets [nlevels_bwd + 1].  level(k) = 1 + max level of the rows j < k (fwd; j > k bwd) stored in row k. */
+    const int32_t *gs_rows;
+    const int32_t *h_gs_offsets;
+    int32_t gs_nlevels_fwd, gs_nlevels_bwd;
 } dgb_operator;
 
 #define DGB_FLAG_PERIODIC_I 1
@@ -130,6 +137,13 @@ int dgb_bsr_residual(const dgb_operator *h_op, const double *rhs, const double *
  * are evaluated: half the traffic of dgb_bsr_residual.  DG 5-point stencil only. */
 int dgb_bsr_residual_colour(const dgb_operator *h_op, const double *rhs, const double *x, double *r, int32_t relaxed,
                             int32_t shift, double *partials, double *sumsq, const int32_t *skip, void *stream);
+
+/* C = A B for BSR matrices with b x b blocks on a given structure of C (c_indptr / c_indices, any order inside a
+ * row): every stored block of C is the sum over k of A_ik B_kj; replaces  grid.BSR_block_D @ grid.BSR_block_G
+ * (dgfem/relaxation.py:240). */
+int dgb_bsr_spgemm(int32_t b, int32_t n_brow, const int32_t *a_indptr, const int32_t *a_indices, const double *a_data,
+                   const int32_t *b_indptr, const int32_t *b_indices, const double *b_data, const int32_t *c_indptr,
+                   const int32_t *c_indices, double *c_data, void *stream);
 
 /* sum(v^2) of a plain vector into *sumsq (device scalar). */
 int dgb_sumsq(const double *v, int64_t n, double *partials, double *sumsq, void *stream);

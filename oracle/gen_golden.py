@@ -70,6 +70,10 @@ CASES = {
                          mode="stokes", dump="full"),
     "stokes_circ4": dict(grid="CircleInCircle_4X4_nPoly2.xyz", pg=2, pu=2, pp=1, ogrid=True, circ=True, sigmul=2.0,
                          mode="stokes", dump="full"),
+    # Stokes, global ordering + distributive Gauss-Seidel (lsq splitting), the `-s --smoother
+    # distributive_gauss_seidel` run of dgfem/solver.py:61-66 (315 outer iterations)
+    "stokes_dgs_rect4": dict(grid="Rectangle_4X4_nPoly2.xyz", pg=2, pu=2, pp=1, ogrid=False, circ=False, sigmul=1.0,
+                             mode="stokes_dgs", dump="full"),
 }
 
 
@@ -249,6 +253,34 @@ def worker(name):
         u0 = np.sin(0.37 * np.arange(n)) * 0.1
         out["smooth_u0"] = u0
         out["A_u0_fine"] = B @ u0
+    elif case["mode"] == "stokes_dgs":
+        import glob
+        import pickle
+        from dgfem.relaxation import Relaxation
+        params["problem"]["type"] = "Stokes"
+        params["solution"]["p"]["polynomial degree"] = case["pp"]
+        params["solution"]["ordering"] = "global"
+        s = Settings(params)
+        d = DGFEM(settings=s, solve_smoother=True, smoother="distributive_gauss_seidel")
+        g = d.grids[-1]
+        out["nlevels"] = np.int64(1)
+        for nm in ("A", "D", "G"):
+            B = getattr(g, "BSR_block_" + nm)
+            out[f"{nm}_indptr"], out[f"{nm}_indices"] = np.asarray(B.indptr, np.int32), np.asarray(B.indices, np.int32)
+            out[f"{nm}_data"], out[f"{nm}_shape"] = np.asarray(B.data), np.array(B.shape + B.blocksize, np.int64)
+        out["BSR_blocksize"] = np.array(g.BSR.blocksize, np.int64)
+        out["RHS"] = np.asarray(g.RHS)
+        # one and three outer iterations, then the full run (solver.py:63: max_iterations=1000000, splitting='lsq')
+        for its in (1, 3):
+            out[f"dgs_u_{its}"] = np.asarray(Relaxation.distributive_gauss_seidel(
+                g, g.RHS, max_iterations=its, splitting="lsq", settings=s))
+        DG = g.BSR_block_DG
+        out["DG_indptr"], out["DG_indices"] = np.asarray(DG.indptr, np.int32), np.asarray(DG.indices, np.int32)
+        out["DG_data"], out["DG_shape"] = np.asarray(DG.data), np.array(DG.shape + DG.blocksize, np.int64)
+        u = d.solver.solve()
+        out["dgs_u_final"] = np.asarray(u)
+        f = glob.glob("postprocessing/pickles/relaxation/*.pkl")
+        out["dgs_residuals"] = np.asarray(pickle.load(open(f[0], "rb")), dtype=np.float64)
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, f"{name}.npz"), **out)
     shutil.rmtree(w, ignore_errors=True)

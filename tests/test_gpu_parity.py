@@ -550,3 +550,48 @@ def test_midsize_vcycle_against_oracle():
     u1 = d.solver.multigrid_V_cycle(k=len(d.grids), RHS=fine.RHS, u=np.zeros_like(fine.RHS))
     uo = multigrid.v_cycle(H, multigrid.Schedule(), len(H.levels), fo.RHS, np.zeros_like(fo.RHS))
     assert rel_err(u1, uo) < 1e-10
+
+
+def test_stokes_global_order_and_distributive_gauss_seidel():
+    """global-order Stokes blocks (dgfem/discrete_system.py:416-745) and
+    Relaxation.distributive_gauss_seidel with the `lsq` splitting (dgfem/relaxation.py:221-283) -- the
+    `-s --smoother distributive_gauss_seidel` run -- against the reference's output (315 outer
+    iterations, first residuals 0.76194 / 0.46150 / 0.26073)."""
+    import copy
+    from helpers import case_params
+    from dg_multigrid_solver_b200.dgfem import DGFEM
+    from dg_multigrid_solver_b200.grid import Geometry
+    from dg_multigrid_solver_b200.relaxation import Relaxation
+    from dg_multigrid_solver_b200.settings import Settings
+    from dg_multigrid_solver_b200.stokes import Stokes
+    case = CASES["stokes_dgs_rect4"]
+    g = golden("stokes_dgs_rect4")
+    prm = copy.deepcopy(case_params(case))
+    prm["problem"]["type"] = "Stokes"
+    prm["problem"]["include pressure BC"] = False
+    prm["solution"]["p"]["polynomial degree"] = case["pp"]
+    prm["solution"]["ordering"] = "global"
+    s = Settings(prm)
+    d = DGFEM(settings=s, geometry=Geometry(grid_path(case), s), solve_smoother=True,
+              smoother="distributive_gauss_seidel", write_results=False)
+    grid = d.grids[-1]
+    # the regrouped blocks: SciPy's block sizes, stored order and values as the reference has them
+    for nm in ("A", "D", "G"):
+        B = getattr(grid, "BSR_block_" + nm).to_scipy()
+        assert tuple(B.shape) + tuple(B.blocksize) == tuple(int(v) for v in g[f"{nm}_shape"])
+        assert np.array_equal(B.indptr, g[f"{nm}_indptr"]) and np.array_equal(B.indices, g[f"{nm}_indices"])
+        assert rel_err(B.data, g[f"{nm}_data"]) < 1e-12
+    assert tuple(grid.BSR.blocksize) == tuple(int(v) for v in g["BSR_blocksize"])
+    assert rel_err(grid.RHS, g["RHS"]) < 1e-12
+    DG = Stokes(s).block_DG(grid).to_scipy()
+    assert np.array_equal(DG.indptr, g["DG_indptr"]) and np.array_equal(DG.indices, g["DG_indices"])
+    assert rel_err(DG.data, g["DG_data"]) < 1e-12
+    for its in (1, 3):
+        u = Relaxation.distributive_gauss_seidel(grid, grid.RHS, max_iterations=its, splitting="lsq", settings=s)
+        assert rel_err(u, g[f"dgs_u_{its}"]) < 1e-11
+    u = d.solver.solve()                                    # Solver.solve_smoother -> 1e6 iterations, lsq
+    hist = np.array(Relaxation.last_residuals)
+    ref = g["dgs_residuals"]
+    assert len(hist) == len(ref) == 316                     # 315 outer iterations + the converged one
+    assert np.allclose(hist, ref, rtol=1e-8, atol=1e-12)    # 315 accumulated iterations: 1.5e-10 already oracle vs reference
+    assert rel_err(u, g["dgs_u_final"]) < 1e-10

@@ -128,6 +128,30 @@ def test_smoother_only_runs(name):
     assert rel_err(u_fwd, g["block_gauss_seidel_1"]) < 1e-12
 
 
+def test_distributive_gauss_seidel_oracle():
+    """dgoracle.stokes_dgs (restatement of dgfem/relaxation.py:221-283, lsq) on the reference's own global-order
+    blocks reproduces the reference's iterates and its 315-iteration residual history."""
+    import scipy.sparse as sp
+    from dgoracle import stokes_dgs
+    g = golden("stokes_dgs_rect4")
+
+    def M(nm):
+        sh = g[nm + "_shape"]
+        return sp.bsr_array((g[nm + "_data"], g[nm + "_indices"], g[nm + "_indptr"]), shape=(int(sh[0]), int(sh[1])))
+    A, D, G, DG = M("A"), M("D"), M("G"), M("DG")
+    assert (A.blocksize, D.blocksize, G.blocksize, DG.blocksize) == ((6, 6), (4, 4), (4, 4), (4, 4))     # App. B.6
+    assert rel_err((D @ G).toarray(), DG.toarray()) < 1e-14
+    for its in (1, 3):
+        u, _ = stokes_dgs.distributive_gauss_seidel_lsq(A, D, G, g["RHS"], max_iterations=its, DG=DG)
+        assert rel_err(u, g[f"dgs_u_{its}"]) < 1e-13
+    u, hist = stokes_dgs.distributive_gauss_seidel_lsq(A, D, G, g["RHS"], DG=DG)
+    ref = g["dgs_residuals"]
+    assert len(hist) == len(ref) == 316
+    assert np.allclose(ref[:3], [0.76194, 0.46150, 0.26073], rtol=1e-4)
+    assert np.allclose(hist, ref, rtol=1e-8, atol=1e-12)
+    assert rel_err(u, g["dgs_u_final"]) < 1e-12
+
+
 def test_c1_matches_survey_appendix_c():
     """SURVEY.md App. C.1 values (measured with the reference during the survey)."""
     g = golden("c1")
