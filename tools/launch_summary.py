@@ -19,8 +19,8 @@ for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:28]:
     out.append(f"{t/1e3:10.3f} ms {100*t/T:5.1f}%  n={n:5d} avg {t/n:9.1f} us  {k}")
 # last complete cycle: between the last two "entry" helpers on the fine level that start a pre-smoother
 idx = [i for i, (k, g, t) in enumerate(L) if k.startswith('k_gs_helper<9, true') or k.startswith('k_gs_helper<9, 1')]
-if len(idx) >= 4:
-    a, b = idx[-4], idx[-2]
+if len(idx) >= 7:
+    a, b = idx[4], idx[6]        # the third V-cycle of the run (two entry-residual helpers per cycle)
     cyc = collections.defaultdict(lambda: [0, 0.0])
     for k, g, t in L[a:b]:
         cyc[k][0] += 1; cyc[k][1] += t

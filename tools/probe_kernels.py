@@ -83,6 +83,9 @@ def main():
         "gs_bwd": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, -1, 0, None, st), ab["gs_pass"]),
         "entry_residual": (lambda: L.dgb_block_gs_entry_residual(__import__("ctypes").byref(op), _lib.ptr(g.d_rhs), _lib.ptr(x), 1,
                                                                  _lib.ptr(y), _lib.ptr(part), _lib.ptr(ss), st), ab["residual"]),
+        "rec_residual": (lambda: (_lib.call("dgb_block_gs_pass", op, g.d_rhs, x, -1, 0, None, st),
+                                  L.dgb_block_gs_residual_after_pass(__import__("ctypes").byref(op), _lib.ptr(x), -1, _lib.ptr(y),
+                                                                     _lib.ptr(part), _lib.ptr(ss), None, st)), ab["residual"]),
         "redblack": (lambda: _lib.call("dgb_block_gs_pass", op, g.d_rhs, x, 1, 1, None, st), ab["gs_pass"]),
         "jacobi": (lambda: _lib.call("dgb_block_relax_sweep", op, g.d_rhs, x, y, 1.0, st), ab["gs_pass"]),
     }
