@@ -20,6 +20,8 @@
 
 namespace dgb {
 
+extern int g_gs_variant;
+
 // ---------------------------------------------------------------------------------------
 // K0: one thread per (element, point); point < nq: volume point, else face point.
 __global__ void __launch_bounds__(128)
@@ -332,6 +334,279 @@ k_assemble_poisson(TabView T, const double *__restrict__ vol, const double *__re
     }
 }
 
+// =========================================================================================
+// K1+K2 on the FP64 tensor cores (b >= 16, i.e. p >= 3).
+//
+// Every block of an element row is a sum over "points" t of outer products, C[k][l] = sum_t L[t][k] R[t][l]:
+//   mass      L = w J V,                 R = V                                    (nq points)
+//   diagonal  L = nu w J Dx | nu w J Dy | W Vt      | -c st W dnO                 (2 nq + 8 nq1 points)
+//             R = Dx        | Dy        | pen Vt - c st dnO | Vt
+//   neighbour L = W Vt                  | c st W dnO                              (2 nq1 points per face)
+//             R = -c st dnN - pen Vn    | Vn
+//   out       = Minv blk  with L = Minv (symmetric), R = blk                      (b points)
+// (the same terms k_assemble_poisson sums entry by entry; face.py:115-280, element.py:181-199).  The point tables
+// are built in shared memory by the whole CTA, the products run as DMMA m8n8k4 (`mma.sync ... f64`): tile (I, J) of
+// C takes its A fragment from L[t0 + lane%4][8I + lane/4] and its B fragment from R[t0 + lane%4][8J + lane/4].
+// Measured on the p=5 contraction: 24.4 TFLOP/s against 5.0 for the per-entry loop and 10.0 for 4 x 4 register
+// tiles (profiles/r02_dmma_vs_dfma.md).  The mass matrix is inverted by the whole CTA (Gauss-Jordan, partial
+// pivoting), not by one warp.
+template <int BT>
+struct MmaCfg {
+    static constexpr int BS = BT == 36 ? 36 : BT == 25 ? 28 : 20;       // row stride of the tables: rows 32 / 96 bytes apart (mod 128)
+    static constexpr int NTL = (BT + 7) / 8;                             // 8 x 8 tiles per direction
+    static constexpr int NT2 = NTL * NTL;
+    static constexpr int MAXT = (NT2 + 7) / 8;                           // tiles per warp (8 warps)
+    static constexpr int B4 = (BT + 3) & ~3;                             // b rounded up to the DMMA k-step
+};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int BT>
+__device__ __forceinline__ void mma_lr(double (&acc)[MmaCfg<BT>::MAXT][2], const double *L, const double *R, int tcount,
+                                       int warp, int lane) {
+    using C = MmaCfg<BT>;
+    const int m = lane >> 2, kk = lane & 3;
+    for (int t0 = 0; t0 < tcount; t0 += 4) {
+        const double *l = L + (t0 + kk) * C::BS + m, *r = R + (t0 + kk) * C::BS + m;
+#pragma unroll
+        for (int s = 0; s < C::MAXT; ++s) {
+            const int tile = warp + 8 * s;
+            if (tile < C::NT2) dmma884(acc[s], l[8 * (tile / C::NTL)], r[8 * (tile % C::NTL)]);
+        }
+    }
+}
+// C tiles -> dst[row * stride + col] (rows, cols < b); lane holds C[m][2 kk], C[m][2 kk + 1]
+template <int BT>
+__device__ __forceinline__ void mma_store(const double (&acc)[MmaCfg<BT>::MAXT][2], double *dst, int stride, int warp,
+                                          int lane) {
+    using C = MmaCfg<BT>;
+    const int m = lane >> 2, kk = lane & 3;
+#pragma unroll
+    for (int s = 0; s < C::MAXT; ++s) {
+        const int tile = warp + 8 * s;
+        if (tile >= C::NT2) continue;
+        const int row = 8 * (tile / C::NTL) + m, col = 8 * (tile % C::NTL) + 2 * kk;
+        if (row < BT && col < BT) dst[row * stride + col] = acc[s][0];
+        if (row < BT && col + 1 < BT) dst[row * stride + col + 1] = acc[s][1];
+    }
+}
+
+// in-place Gauss-Jordan inverse with partial pivoting by the whole CTA (256 threads), matrix a[b][stride] in smem
+template <int BT>
+__device__ void cta_invert(double *a, int stride, double *col, int *piv, int *s_p) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < BT; ++k) {
+        if (tid < 32) {                        // first maximum of |a[i][k]|, i >= k
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < BT; i += 32) {
+                const double v = fabs(a[i * stride + k]);
+                if (v > best) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (tid == 0) { *s_p = bi; piv[k] = bi; }
+        }
+        __syncthreads();
+        const int p = *s_p;
+        if (p != k && tid < BT) {
+            const double t = a[k * stride + tid];
+            a[k * stride + tid] = a[p * stride + tid];
+            a[p * stride + tid] = t;
+        }
+        __syncthreads();
+        if (tid < BT) col[tid] = a[tid * stride + k];
+        __syncthreads();
+        const double pinv = 1.0 / col[k];
+        if (tid < BT) a[k * stride + tid] = (tid == k) ? pinv : a[k * stride + tid] * pinv;
+        __syncthreads();
+        for (int t = tid; t < BT * BT; t += 256) {
+            const int i = t / BT, c = t - i * BT;
+            if (i == k) continue;
+            a[i * stride + c] = (c == k) ? -col[i] * pinv : fma(-col[i], a[k * stride + c], a[i * stride + c]);
+        }
+        __syncthreads();
+    }
+    for (int k = BT - 1; k >= 0; --k) {        // undo the row interchanges as column interchanges
+        const int p = piv[k];
+        if (p != k && tid < BT) {
+            const double t = a[tid * stride + k];
+            a[tid * stride + k] = a[tid * stride + p];
+            a[tid * stride + p] = t;
+        }
+        __syncthreads();
+    }
+}
+
+template <int BT, int QT>
+__global__ void __launch_bounds__(256)
+k_assemble_poisson_mma(TabView T, const double *__restrict__ vol, const double *__restrict__ face,
+                       const double *__restrict__ area, Stencil S, double nu, double sigma, int use_minv,
+                       int32_t *__restrict__ indptr, int32_t *__restrict__ indices, double *__restrict__ data,
+                       double *__restrict__ minv_out) {
+    using C = MmaCfg<BT>;
+    constexpr int b = BT, nq1 = QT, nq = QT * QT, bb = BT * BT, BS = C::BS, B4 = C::B4;
+    constexpr int NQ4 = (nq + 3) & ~3;                  // volume points rounded up to the k-step
+    constexpr int TCF = (2 * nq1 + 3) & ~3;             // rows per face in the neighbour tables
+    constexpr int TC = NQ4 > 8 * nq1 ? (NQ4 > 4 * TCF ? NQ4 : 4 * TCF) : (8 * nq1 > 4 * TCF ? 8 * nq1 : 4 * TCF);
+    extern __shared__ __align__(16) double sm[];
+    double *Lt = sm;                          // [TC][BS] + 8
+    double *Rt = Lt + TC * BS + 8;            // [TC][BS] + 8
+    double *Mi = Rt + TC * BS + 8;            // [B4][BS] + 8: mass matrix, then its inverse
+    double *Bk = Mi + B4 * BS + 8;            // [B4][BS] + 8: the block being assembled
+    double *colv = Bk + B4 * BS + 8;          // [B4]
+    __shared__ FaceInfo fi[4];
+    __shared__ int s_cols[5], s_rank[5], s_piv[64], s_p;
+    __shared__ int64_t s_row0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = S.Ni * S.Nj;
+    // zero everything once: padding rows / columns of the tables stay zero for the whole kernel
+    for (int t = tid; t < 2 * (TC * BS + 8) + 2 * (B4 * BS + 8) + B4; t += 256) sm[t] = 0.0;
+    __syncthreads();
+    for (int e = blockIdx.x; e < N; e += gridDim.x) {
+        const int i = e % S.Ni, j = e / S.Ni;
+        if (!S.active(j)) {       // ghost row of a slab: an empty matrix row
+            if (tid == 0) {
+                indptr[e] = (int32_t)S.row_start(i, j);
+                if (e == N - 1) indptr[N] = (int32_t)S.row_start(0, S.Nj);
+            }
+            continue;
+        }
+        if (tid == 0) {
+            int c[5], rk[5];
+            S.cols(i, j, c);
+            slot_ranks(c, rk);
+            for (int s = 0; s < 5; ++s) { s_cols[s] = c[s]; s_rank[s] = rk[s]; }
+            s_row0 = S.row_start(i, j);
+            const double Ae = area[e];
+            for (int f = 0; f < 4; ++f) {
+                const int nb = c[1 + f];
+                FaceInfo q;
+                q.nbr = nb;
+                q.st = (f & 1) ? 1.0 : -1.0;
+                const double hF = nb >= 0 ? 0.5 * (sqrt(Ae) + sqrt(area[nb])) : sqrt(Ae);   // face.py:14,21,28
+                q.pen = sigma * nu / hF;
+                q.c_nu = (nb >= 0 ? 0.5 : 1.0) * nu;
+                fi[f] = q;
+            }
+        }
+        const double *ve = vol + (size_t)e * VOL_NC * nq;
+        double acc[C::MAXT][2];
+        auto zero_acc = [&]() {
+#pragma unroll
+            for (int s = 0; s < C::MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
+        };
+        // ---- mass matrix: L = w J V, R = V ----
+        for (int t = tid; t < nq * b; t += 256) {
+            const int q = t / b, k = t - q * b;
+            const double v = T.V[t];
+            Lt[q * BS + k] = v * (ve[q] * T.w2[q]);
+            Rt[q * BS + k] = v;
+        }
+        for (int t = tid; t < (NQ4 - nq) * BS; t += 256) Lt[nq * BS + t] = Rt[nq * BS + t] = 0.0;
+        __syncthreads();
+        zero_acc();
+        mma_lr<BT>(acc, Lt, Rt, NQ4, warp, lane);
+        mma_store<BT>(acc, Mi, BS, warp, lane);
+        __syncthreads();
+        cta_invert<BT>(Mi, BS, colv, s_piv, &s_p);
+        for (int t = tid; t < bb; t += 256) minv_out[(size_t)e * bb + t] = Mi[(t / b) * BS + (t % b)];
+        // out = Minv * Bk (or Bk), written as the block of sorted rank rk of this row
+        auto emit = [&](int rk) {
+            double *dst = data + ((size_t)s_row0 + rk) * bb;
+            if (use_minv) {
+                zero_acc();
+                mma_lr<BT>(acc, Mi, Bk, B4, warp, lane);
+                mma_store<BT>(acc, dst, b, warp, lane);
+            } else {
+                for (int t = tid; t < bb; t += 256) dst[t] = Bk[(t / b) * BS + (t % b)];
+            }
+        };
+        // ---- diagonal block: volume part in two chunks (x-, y-derivative), then the four faces ----
+        zero_acc();
+        for (int part = 0; part < 2; ++part) {
+            __syncthreads();
+            for (int t = tid; t < nq * b; t += 256) {
+                const int q = t / b, k = t - q * b;
+                const double d = T.Vr[t] * ve[(1 + 2 * part) * nq + q] + T.Vs[t] * ve[(2 + 2 * part) * nq + q];   // element.py:182-193
+                Lt[q * BS + k] = nu * (ve[q] * T.w2[q]) * d;
+                Rt[q * BS + k] = d;
+            }
+            __syncthreads();
+            mma_lr<BT>(acc, Lt, Rt, NQ4, warp, lane);
+        }
+        __syncthreads();
+        for (int t = tid; t < 4 * nq1 * b; t += 256) {
+            const int f = t / (nq1 * b), rem = t - f * nq1 * b;
+            const int q = rem / b, k = rem - q * b;
+            const int nb = fi[f].nbr;
+            const double *fo = face + ((size_t)e * 4 + f) * FACE_NC * nq1;
+            double Jf = fo[q];
+            if (!(f & 1) && nb >= 0)       // min face with an L neighbour: use L's max-face J (face.py:15,22,30)
+                Jf = face[((size_t)nb * 4 + opp_face(f)) * FACE_NC * nq1 + q];
+            const double W = Jf * T.w1[q];
+            const int tr = own_trace(f);
+            const size_t ti = ((size_t)tr * nq1 + q) * b + k;
+            const double vt = T.Vf[ti];
+            const double dn = T.Vrf[ti] * fo[nq1 + q] + T.Vsf[ti] * fo[2 * nq1 + q];
+            const double cst = fi[f].c_nu * fi[f].st;
+            const int r0 = (f * 2) * nq1 + q, r1 = (f * 2 + 1) * nq1 + q;
+            Lt[r0 * BS + k] = W * vt;           Rt[r0 * BS + k] = fi[f].pen * vt - cst * dn;
+            Lt[r1 * BS + k] = -cst * W * dn;    Rt[r1 * BS + k] = vt;
+        }
+        __syncthreads();
+        mma_lr<BT>(acc, Lt, Rt, 8 * nq1, warp, lane);
+        mma_store<BT>(acc, Bk, BS, warp, lane);
+        __syncthreads();
+        emit(s_rank[0]);
+        __syncthreads();
+        // ---- neighbour blocks: tables of all four faces at once, one product per existing neighbour ----
+        for (int t = tid; t < 4 * TCF * BS; t += 256) Lt[t] = Rt[t] = 0.0;
+        __syncthreads();
+        for (int t = tid; t < 4 * nq1 * b; t += 256) {
+            const int f = t / (nq1 * b), rem = t - f * nq1 * b;
+            const int q = rem / b, k = rem - q * b;
+            const int nb = fi[f].nbr;
+            if (nb < 0) continue;
+            const double *fo = face + ((size_t)e * 4 + f) * FACE_NC * nq1;
+            const double *fn = face + ((size_t)nb * 4 + opp_face(f)) * FACE_NC * nq1;
+            const double Jf = (f & 1) ? fo[q] : fn[q];
+            const double W = Jf * T.w1[q];
+            const size_t to = ((size_t)own_trace(f) * nq1 + q) * b + k, tn = ((size_t)f * nq1 + q) * b + k;
+            const double vt = T.Vf[to], vn = T.Vf[tn];
+            const double dO = T.Vrf[to] * fo[nq1 + q] + T.Vsf[to] * fo[2 * nq1 + q];
+            const double dN = T.Vrf[tn] * fn[nq1 + q] + T.Vsf[tn] * fn[2 * nq1 + q];
+            const double cst = fi[f].c_nu * fi[f].st;
+            const int r0 = f * TCF + q, r1 = f * TCF + nq1 + q;
+            Lt[r0 * BS + k] = W * vt;           Rt[r0 * BS + k] = -cst * dN - fi[f].pen * vn;
+            Lt[r1 * BS + k] = cst * W * dO;     Rt[r1 * BS + k] = vn;
+        }
+        __syncthreads();
+        for (int f = 0; f < 4; ++f) {
+            if (fi[f].nbr < 0) continue;          // uniform over the CTA
+            zero_acc();
+            mma_lr<BT>(acc, Lt + f * TCF * BS, Rt + f * TCF * BS, TCF, warp, lane);
+            mma_store<BT>(acc, Bk, BS, warp, lane);
+            __syncthreads();
+            emit(s_rank[1 + f]);
+            __syncthreads();
+        }
+        if (tid < 5 && s_rank[tid] >= 0) indices[s_row0 + s_rank[tid]] = s_cols[tid];
+        if (tid == 0) {
+            indptr[e] = (int32_t)s_row0;
+            if (e == N - 1) indptr[N] = (int32_t)S.row_start(0, S.Nj);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K3: one warp-group of b threads per element would under-fill; use one CTA (64 thr) / element
 __global__ void __launch_bounds__(64)
@@ -495,13 +770,30 @@ int dgb_assemble_poisson(const dgb_tables *t, const double *vol, const double *f
     } while (0)
     // (p+1)^2 blocks with the reference's N_int = 3p/2 + 1 points per direction (grid.py:107); anything else
     // (e.g. another integration-order factor) takes the runtime-sized instance
-    if (T.b == 4 && T.nq1 == 2) DGB_ASM_LAUNCH(4, 2);
+#define DGB_ASM_LAUNCH_MMA(BT, QT)                                                                              \
+    do {                                                                                                        \
+        constexpr int NQ4 = (QT * QT + 3) & ~3, TCF = (2 * QT + 3) & ~3, BS = MmaCfg<BT>::BS, B4 = MmaCfg<BT>::B4;  \
+        constexpr int TC = NQ4 > 8 * QT ? (NQ4 > 4 * TCF ? NQ4 : 4 * TCF) : (8 * QT > 4 * TCF ? 8 * QT : 4 * TCF);  \
+        const size_t sm2 = sizeof(double) * (2 * (TC * BS + 8) + 2 * (B4 * BS + 8) + B4);                       \
+        DGB_CUDA_OK(cudaFuncSetAttribute(k_assemble_poisson_mma<BT, QT>,                                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));               \
+        k_assemble_poisson_mma<BT, QT><<<(int)g, 256, sm2, st>>>(T, vol, face, area, S, nu, sigma, um, indptr, \
+                                                                 indices, data, minv);                          \
+    } while (0)
+    // b >= 16 with the reference's quadrature: the contractions run on the FP64 tensor cores (DMMA); tuning value
+    // dgb_set_kernel_path(100 + 51) keeps the per-entry DFMA kernel (for the comparison in profiles/)
+    const bool mma = dgb::g_gs_variant != 51;
+    if (mma && T.b == 16 && T.nq1 == 5) DGB_ASM_LAUNCH_MMA(16, 5);
+    else if (mma && T.b == 25 && T.nq1 == 7) DGB_ASM_LAUNCH_MMA(25, 7);
+    else if (mma && T.b == 36 && T.nq1 == 8) DGB_ASM_LAUNCH_MMA(36, 8);
+    else if (T.b == 4 && T.nq1 == 2) DGB_ASM_LAUNCH(4, 2);
     else if (T.b == 9 && T.nq1 == 4) DGB_ASM_LAUNCH(9, 4);
     else if (T.b == 16 && T.nq1 == 5) DGB_ASM_LAUNCH(16, 5);
     else if (T.b == 25 && T.nq1 == 7) DGB_ASM_LAUNCH(25, 7);
     else if (T.b == 36 && T.nq1 == 8) DGB_ASM_LAUNCH(36, 8);
     else DGB_ASM_LAUNCH(0, 0);
 #undef DGB_ASM_LAUNCH
+#undef DGB_ASM_LAUNCH_MMA
     DGB_LAUNCH_OK();
     return 0;
 }

@@ -41,6 +41,8 @@ def main():
     s = Settings(prm)
     s.update_setting("solver.method", "smoother")
     s.update_setting("solver.discretization", "dg")
+    if os.environ.get("DGB_GS_VARIANT"):                # tuning switches that also affect the assembly (51: DFMA kernel)
+        _lib.load().dgb_set_kernel_path(100 + int(os.environ["DGB_GS_VARIANT"]))
     geo = Geometry(None, s, nodes=nodes(ni, nj, Pg))
     g = Grid(geo, ["u"]).initialize({"u": p}, None)
     DiscreteSystem(s).problem.assemble(g)
