@@ -27,6 +27,7 @@
 // row-pipelined kernel.
 #include "dgb_async.cuh"
 #include "dgb_common.cuh"
+#include "dgb_mma.cuh"
 
 namespace dgb {
 
@@ -1174,6 +1175,65 @@ k_build_gs_chain(const double *__restrict__ data, const int32_t *__restrict__ in
     }
 }
 
+// The same records for b >= 16 with the products -Dinv_e A_e,n on the FP64 tensor cores: one CTA (8 warps) per
+// element, Dinv^T and the neighbour block staged in shared memory (C = Dinv A: L[t][k] = Dinv[k][t], R[t][l] = A[t][l]).
+template <int B>
+__global__ void __launch_bounds__(256)
+k_build_gs_chain_mma(const double *__restrict__ data, const int32_t *__restrict__ indices,
+                     const int32_t *__restrict__ indptr, const double *__restrict__ dinv, Stencil S_, double *rec) {
+    using M = MmaCfg<B>;
+    constexpr int B2 = B * B, REC = ChainCfg<B>::REC, BS = M::BS, B4 = M::B4;
+    __shared__ __align__(16) double Lt[B4 * BS + 8], Rt[B4 * BS + 8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Ni = S_.Ni, N = Ni * S_.Nj;
+    for (int t = tid; t < B4 * BS + 8; t += 256) Lt[t] = Rt[t] = 0.0;
+    __syncthreads();
+    const int nslots = S_.per_i ? 6 : 4;          // 4 record blocks + the two wrap blocks of the row ends
+    for (int e = blockIdx.x; e < N; e += gridDim.x) {
+        const int j = e / Ni, i = e - j * Ni;
+        if (!S_.active(j)) continue;
+        for (int t = tid; t < B2; t += 256) Lt[(t % B) * BS + t / B] = dinv[(size_t)e * B2 + t];     // Dinv^T
+        for (int slot = 0; slot < nslots; ++slot) {
+            const int dir = (slot & 2) ? -1 : 1;
+            int col = -1;
+            double *dst = nullptr;
+            if (slot < 4) {
+                if ((slot & 1) == 0) col = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;
+                else col = S_.active(j - dir) ? e - dir * Ni : -1;
+                dst = rec + ((size_t)(slot >> 1) * chain_dir_records<B>(S_) + (size_t)chain_loc<B>(S_, dir, i, j)) * REC + (slot & 1) * B2;
+            } else {                               // wrap[d01][row j]: the row's last element meets its first one
+                const int d01 = slot - 4, wd = d01 == 0 ? 1 : -1;
+                if (i == (wd > 0 ? Ni - 1 : 0)) {
+                    col = j * Ni + (wd > 0 ? 0 : Ni - 1);
+                    dst = rec + 2 * (size_t)chain_dir_records<B>(S_) * REC + ((size_t)d01 * S_.Nj + j) * B2;
+                }
+            }
+            int jj = -1;
+            if (col >= 0)
+                for (int q = indptr[e]; q < indptr[e + 1]; ++q)
+                    if (indices[q] == col) jj = q;
+            __syncthreads();                       // Lt complete / the previous slot's products are done with Rt
+            if (jj < 0) continue;                  // no such neighbour: the record block stays zero (uniform over the CTA)
+            for (int t = tid; t < B2; t += 256) Rt[(t / B) * BS + t % B] = data[(size_t)jj * B2 + t];
+            __syncthreads();
+            double acc[M::MAXT][2];
+#pragma unroll
+            for (int s = 0; s < M::MAXT; ++s) acc[s][0] = acc[s][1] = 0.0;
+            mma_lr<B>(acc, Lt, Rt, B4, warp, lane);
+            const int m = lane >> 2, kk = lane & 3;
+#pragma unroll
+            for (int s = 0; s < M::MAXT; ++s) {
+                const int tile = warp + 8 * s;
+                if (tile >= M::NT2) continue;
+                const int row = 8 * (tile / M::NTL) + m, c0 = 8 * (tile % M::NTL) + 2 * kk;
+                if (row < B && c0 < B) dst[ChainCfg<B>::mat_offset(row, c0)] = -acc[s][0];
+                if (row < B && c0 + 1 < B) dst[ChainCfg<B>::mat_offset(row, c0 + 1)] = -acc[s][1];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // block sizes the chained kernel is used for: bit 0 b=4, bit 1 b=9, bit 2 b=16, bit 3 b=25, bit 4 b=36
@@ -1491,9 +1551,19 @@ int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
     switch (op->b) {
     case 4: k_build_gs_chain<4><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
     case 9: k_build_gs_chain<9><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
-    case 16: k_build_gs_chain<16><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
-    case 25: k_build_gs_chain<25><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
-    case 36: k_build_gs_chain<36><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain); break;
+    // b >= 16: the products run on the FP64 tensor cores (dgb_set_kernel_path(100 + 51) keeps the per-entry kernel)
+    case 16:
+        if (g_gs_variant != 51) k_build_gs_chain_mma<16><<<(int)(N < sm_count() * 8 ? N : sm_count() * 8), 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        else k_build_gs_chain<16><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        break;
+    case 25:
+        if (g_gs_variant != 51) k_build_gs_chain_mma<25><<<(int)(N < sm_count() * 8 ? N : sm_count() * 8), 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        else k_build_gs_chain<25><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        break;
+    case 36:
+        if (g_gs_variant != 51) k_build_gs_chain_mma<36><<<(int)(N < sm_count() * 8 ? N : sm_count() * 8), 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        else k_build_gs_chain<36><<<(int)g, 256, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, S_, op->gs_chain);
+        break;
     }
     DGB_LAUNCH_OK();
     return 0;

@@ -90,6 +90,8 @@ class DGFEM:
         else:
             self.grids.append(Grid(self.geometry, self.vars, s.solver.discretization).initialize(self.P_sol, self.sigma))
         discrete_system = DiscreteSystem(s)
+        from .discrete_system import SETUP_TIMINGS
+        SETUP_TIMINGS["smoother_setup"] = 0.0
         with Timer() as t:
             if s.solver.method == "multigrid":
                 for grid in self.grids:                      # dgfem.py:121-123 (every level, RHS included)
@@ -97,7 +99,10 @@ class DGFEM:
             else:
                 discrete_system.problem.assemble(self.grids[-1])
             _lib.require_cuda().cuda.synchronize()
-        self.timings["assemble"] = t.elapsed()
+        # `assemble` = what the reference's assemble() does (metrics, operator, right-hand side); the inverse
+        # diagonal blocks and smoother records are this implementation's own setup phase
+        self.timings["smoother_setup"] = SETUP_TIMINGS["smoother_setup"]
+        self.timings["assemble"] = t.elapsed() - self.timings["smoother_setup"]
         self.solver.grids = self.grids
 
     def assemble_multigrid_operators(self):

@@ -100,9 +100,26 @@ class Poisson:
         assert T.b == b
 
 
+# seconds spent in prepare_smoother_data since the last reset (the reference has no such phase: pyamg rebuilds the
+# inverse diagonal blocks inside every smoother call); DGFEM.initialize reports it beside the assembly time
+SETUP_TIMINGS = {"smoother_setup": 0.0}
+
+
 def prepare_smoother_data(grid):
     """Inverse diagonal blocks and the smoother stream, once per level (the reference recomputes
     the block inverses on every smoother call: pyamg_relaxation.py:230-231)."""
+    import time
+    torch = _lib.require_cuda()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    try:
+        return _prepare_smoother_data(grid)
+    finally:
+        torch.cuda.synchronize()
+        SETUP_TIMINGS["smoother_setup"] += time.perf_counter() - t0
+
+
+def _prepare_smoother_data(grid):
     torch = _lib.require_cuda()
     from .grid import padded_blocks
     b = grid.d_data.shape[1]
