@@ -54,7 +54,10 @@ struct ChainCfg {
     __host__ __device__ static constexpr int mat_offset(int r, int c) {
         return ((c % CW) / MV) * (LPR * MV) + (r * P + c / CW) * MV + (c % CW) % MV;
     }
-    static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, c, d}, 16-byte multiple
+    static constexpr int REC = (2 * B2 + 2 * B + 1) & ~1;             // doubles per record {M_row, M_up, (c, d) pairs}, 16-byte multiple
+    // c_r and d_r of a record sit next to each other (one 16-byte load brings both)
+    __host__ __device__ static constexpr int c_off(int r) { return 2 * B2 + 2 * r; }
+    __host__ __device__ static constexpr int d_off(int r) { return 2 * B2 + 2 * r + 1; }
     static constexpr int CH = B <= 9 ? 8 : B <= 16 ? 4 : 1;           // steps per chunk (one bulk copy)
     static constexpr int NS = (B == 9 || B == 16 || B == 36) ? 2 : 3; // bulk-copy stages
     static constexpr int RING = B <= 9 ? 32 : 16;                     // columns per band hand-over ring
@@ -130,13 +133,6 @@ __device__ __forceinline__ void chain_load_vec(uint32_t a, double (&v)[ChainCfg<
         *any_sentinel = mx == 0xffffffffu;
     }
 }
-// the "not delivered" test of the fast path: every lane of an element row looks at the high word of ONE entry of
-// the slot (entry part*CW + r % CW: the lanes of a row cover all B entries), a warp vote does the rest
-__device__ __forceinline__ uint32_t lds_u32v(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
 // my part of one ring slot, volatile loads (ordered after the delivery test)
 template <int B>
 __device__ __forceinline__ void chain_load_vec_v(uint32_t a, double (&v)[ChainCfg<B>::VN]) {
@@ -162,8 +158,9 @@ struct ChainRow {
     // the same through volatile loads: ptxas keeps them behind the (volatile) loads of the ring slots
     __device__ __forceinline__ void load_v(uint32_t rm, uint32_t rc) {
         constexpr int B2 = B * B;
-        c = lds1v(rc);
-        d = lds1v(rc + B * 8);
+        const double2 cdv = lds2v(rc);
+        c = cdv.x;
+        d = cdv.y;
         constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
         if (MV == 2) {
 #pragma unroll
@@ -182,8 +179,9 @@ struct ChainRow {
     }
     __device__ __forceinline__ void load(uint32_t rm, uint32_t rc) {
         constexpr int B2 = B * B;
-        c = lds1(rc);
-        d = lds1(rc + B * 8);
+        const double2 cdv = lds2(rc);
+        c = cdv.x;
+        d = cdv.y;
         // lane-major layout: my k-th entry is LPR * MV doubles after my (k - MV)-th
         constexpr int MV = ChainCfg<B>::MV, LS = ChainCfg<B>::LPR * MV;
         if (MV == 2) {
@@ -459,16 +457,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     uint32_t out_w = lastg ? (succ == 3 ? cluster_map(smem_u32(rings), crank + 1) : cluster_map(smem_u32(outr), crank)) + 8 * r
                            : cluster_map(scr, crank) + 8 * lane;
     const uint32_t po = (uint32_t)(part * CW * 8);                     // my columns inside a ring slot
-    const uint32_t co = (uint32_t)((part * CW + r % CW) * 8 + 4);      // high word of the slot entry I test for delivery
     const uint32_t prog_next = succ == 3 ? cluster_map(smem_u32((const void *)&s_prog[0]), crank + 1)
                                          : cluster_map(smem_u32((const void *)&s_prog[w + 1]), crank);
-    uint32_t sen_w = (fin && first_row) ? in_b + 8 * r : scr + 8 * lane;         // row 0 hands the incoming slot back
     uint32_t rec_m = smem_u32(wstage) + (uint32_t)((gq * REC + C::mat_offset(r, part * CW)) * 8);   // my first matrix entry, stage 0 step 0
-    uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + 2 * B2 + r) * 8); // my c
+    uint32_t rec_c = smem_u32(wstage) + (uint32_t)((gq * REC + C::c_off(r)) * 8); // my (c, d) pair
     uint32_t own_w = fin ? own_b + 8 * r : scr + 8 * lane;
-    const uint32_t first_mask = (fin && first_row) ? 0xffffffffu : 0u;
     asm volatile("" : "+r"(in_b), "+r"(up_b), "+r"(own_b), "+r"(out_w));
-    asm volatile("" : "+r"(sen_w), "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
+    asm volatile("" : "+r"(rec_m), "+r"(rec_c), "+r"(own_w));
     double *xrow = x + (size_t)j * Ni * B + r;
     // O-grid: the block that couples a row's last element to its first one (wrapm[row][B2], lane-major like the
     // record blocks) is staged in shared memory once per band; the first element's new value is parked beside it
@@ -489,7 +484,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     {
         const int sro = nrows - 1 - (sr0 + gq);                // my row in the opposite sweep order
         const int bo = sro / R, go = sro - bo * R;
-        corow = rec_other + (((size_t)bo * (Ni + R - 1) + (Ni - 1) + go) * R + go) * REC + 2 * B2 + r;   // idx = 0
+        corow = rec_other + (((size_t)bo * (Ni + R - 1) + (Ni - 1) + go) * R + go) * REC + C::c_off(r);   // idx = 0
     }
     constexpr long long COS = -(long long)R * REC;          // doubles per step
 
@@ -547,13 +542,12 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
                 pa = pa0;
                 ow = own_w + sr0b;
             }
-            uint32_t sw = sen_w + (si0 & first_mask);
             uint32_t oa = out_w + (uint32_t)((t0 - (R - 1)) % RING) * S;      // column-indexed (consumer's view)
             const uint32_t oend = out_w + RING * S;
             double *xp = xrow + (size_t)(DIR > 0 ? t0 - gq : Ni - 1 - (t0 - gq)) * B;
             double *cop = corow + (long long)(t0 - gq) * COS;
             asm volatile("" : "+r"(ua0), "+r"(ua), "+r"(pa0), "+r"(pa));
-            asm volatile("" : "+r"(ow), "+r"(sw), "+r"(sm), "+r"(sc));
+            asm volatile("" : "+r"(ow), "+r"(sm), "+r"(sc));
             asm volatile("" : "+l"(xp), "+l"(cop));
             // software pipeline: the record of step k + 1 is read (plain shared-memory loads, the stage is complete)
             // while the dependent arithmetic of step k waits for its operands
@@ -563,22 +557,23 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
             for (int k = 0; k < CH; ++k) {
                 const uint32_t uk = k == 0 ? ua0 : ua + k * S;     // slot of the row above
                 double u[VN], p[VN];
-                // delivery test BEFORE the data: the lanes of a row test one entry each in ONE warp-wide load, so every
-                // entry seen delivered here is delivered in the (later) loads of u as well
-                const uint32_t hi_u = lds_u32v(uk + co);
                 chain_load_vec_v<B>(uk + po, u);
                 chain_load_vec_v<B>(k == 0 ? pa0 : pa + k * S, p);
                 if (k + 1 < CH) rows[(k + 1) & 1].load_v(sm + (k + 1) * KS, sc + (k + 1) * KS);
                 const ChainRow<B> &row = rows[k & 1];
                 double xnew = row.eval(p, u);
                 // the neighbour band has not delivered this column yet?  (rows above inside the warp always have)
-                const bool wait_up = __any_sync(FULL, hi_u == 0xffffffffu);
+                // delivery test on the loaded registers themselves (no ordering question): some entry of my part of the
+                // slot still carries the all-ones mark?  (P == 1: every lane holds the whole slot)
+                unsigned mxh = 0u;
+#pragma unroll
+                for (int c = 0; c < (P == 1 ? B : VN); ++c) mxh = max(mxh, (unsigned)__double2hiint(u[c]));
+                const bool wait_up = __any_sync(FULL, mxh == 0xffffffffu);
                 if (__builtin_expect(wait_up, 0)) {
                     if (!chain_wait_up<B>(uk, err)) return;
                     chain_load_vec<B>(uk + po, u, nullptr);
                     xnew = row.eval(p, u);
                 }
-                sts1(sw + k * S, sentinel);
                 sts1(ow + k * S, xnew);
                 sts1_cluster(oa, xnew);
                 oa += S;
@@ -589,6 +584,8 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
                 }
                 __syncwarp();
             }
+            // hand the CH consumed slots of the incoming ring back in one go (they are contiguous: RING % CH == 0)
+            for (int q = lane; q < CH * BP; q += 32) sts1(in_b + si0 + 8 * q, sentinel);
         } else {
             // ---- pipeline fill / drain: some rows are outside [0, Ni) ----
 #pragma unroll 1
@@ -678,8 +675,8 @@ template <int B>
 __device__ __forceinline__ double2 big_eval(uint32_t rec_a /* record */, uint32_t pa, uint32_t ua, int q, bool *bad) {
     constexpr int B2 = B * B;
     const uint32_t m = rec_a + (uint32_t)(q * 32);                     // my two rows of a 16-byte column pair
-    const double2 cc = lds2(rec_a + (uint32_t)((2 * B2 + 2 * q) * 8));
-    double a0 = cc.x, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = cc.y, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    const double c0 = lds1(rec_a + (uint32_t)(ChainCfg<B>::c_off(2 * q) * 8)), c1 = lds1(rec_a + (uint32_t)(ChainCfg<B>::c_off(2 * q + 1) * 8));
+    double a0 = c0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = c1, b1 = 0.0, b2 = 0.0, b3 = 0.0;
     unsigned mx = 0u;
 #pragma unroll
     for (int k = 0; k < B / 2; ++k) {
@@ -803,7 +800,7 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
     const uint32_t stage0 = smem_u32(wstage);
     double *xrow = x + (size_t)j * Ni * B + 2 * q;
     const int sro = nrows - 1 - sr;                                    // my row in the opposite sweep order
-    double *corow = rec_other + ((size_t)sro * Ni + (Ni - 1)) * REC + 2 * B2 + 2 * q;      // idx = 0, stride -REC
+    double *corow = rec_other + ((size_t)sro * Ni + (Ni - 1)) * REC + C::c_off(2 * q);     // idx = 0, stride -REC
     const double *wrow = wrapm + (size_t)j * B2;                       // O-grid: wrap block of my row
     const int per = S_.per_i;
     int prog_seen = 0;
@@ -861,13 +858,15 @@ k_gs_chain_big(const double *__restrict__ rec, double *__restrict__ rec_other, c
             }
         }
         if (live) {
-            const double2 cd = lds2(ra + (uint32_t)((2 * B2 + 2 * q) * 8)), dd = lds2(ra + (uint32_t)((2 * B2 + B + 2 * q) * 8));
+            const double2 v0 = lds2(ra + (uint32_t)(C::c_off(2 * q) * 8)), v1 = lds2(ra + (uint32_t)(C::c_off(2 * q + 1) * 8));
+            const double2 cd = make_double2(v0.x, v1.x), dd = make_double2(v0.y, v1.y);
             sts2(ua + q * 16, make_double2(sentinel, sentinel));                  // hand the incoming slot back
             sts2(row_b + (uint32_t)(t & 1) * S + q * 16, xn);
             sts2_cluster(out_b + (uint32_t)(t % RING) * S + q * 16, xn);
             const int i = DIR > 0 ? t : Ni - 1 - t;
             *reinterpret_cast<double2 *>(xrow + (size_t)i * B) = xn;
-            *reinterpret_cast<double2 *>(corow - (size_t)t * REC) = make_double2((dd.x - cd.x) + xn.x, (dd.y - cd.y) + xn.y);
+            corow[-(long long)t * REC] = (dd.x - cd.x) + xn.x;             // c_next of row 2q; (c, d) pairs: row 2q+1 two doubles on
+            corow[-(long long)t * REC + 2] = (dd.y - cd.y) + xn.y;
             if (succ == 2) {
                 __stcg(mbox + ((size_t)j * Ni + i) * B + 2 * q, xn.x);
                 __stcg(mbox + ((size_t)j * Ni + i) * B + 2 * q + 1, xn.y);
@@ -891,7 +890,7 @@ struct HelperCfg {
 // RES: also evaluate the full residual r = rhs - A x (optionally stored) and its sum of squares (one partial per
 // CTA) -- the smoother's entry residual test (dgfem/relaxation.py:202) shares the block reads of the first pass.
 template <int B, bool RES>
-__global__ void __launch_bounds__(HelperCfg<B>::NT, RES ? 6 : 8)
+__global__ void __launch_bounds__(HelperCfg<B>::NT, RES ? ((B > 4 && B <= 16) ? 5 : 6) : 8)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
             double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
@@ -909,7 +908,13 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int idx = tile * EPB + el;
         const int e = (el < EPB && idx < count) ? first + idx : -1;
+        // my row of Dinv_e: requested now (b <= 16: it fits in registers), used after the barrier
+        // (RES variant, 4 < b <= 16; measured at 2048^2: b = 9 entry residual 3.72 -> 3.20 ms; b = 4 and the plain
+        // helper at 8 CTAs per SM are faster without it)
+        constexpr bool PRE = RES && B > 4 && B <= 16;
+        double dv[PRE ? B : 1];
         if (e >= 0) {
+            if (PRE) load_row<PRE ? B : 1>(dinv + ((size_t)e * B + r) * B, dv);
             const int j = e / Ni, i = e - j * Ni;
             const int e_row = (i - dir >= 0 && i - dir < Ni) ? e - dir : -1;       // handled by the chain
             const int e_up = S_.active(j - dir) ? e - dir * Ni : -1;               // handled by the chain
@@ -942,14 +947,14 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             double tt = 0.0, td = 0.0;
 #pragma unroll
             for (int c = 0; c < B; ++c) {
-                tt = fma(d[c], s_rsum[el * B + c], tt);
-                td = fma(d[c], s_rhs[el * B + c], td);
+                const double dc = PRE ? dv[PRE ? c : 0] : d[c];
+                tt = fma(dc, s_rsum[el * B + c], tt);
+                td = fma(dc, s_rhs[el * B + c], td);
             }
             const int j = e / Ni, i = e - j * Ni;
-            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r;
-            mine[0] = tt;                                   // c_e
-            mine[B] = td;                                   // d_e = Dinv_e rhs_e, for both sweep directions
-            rec_other[(size_t)chain_loc<B>(S_, -dir, i, j) * REC + 2 * B2 + B + r] = td;
+            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + ChainCfg<B>::c_off(r);
+            *reinterpret_cast<double2 *>(mine) = make_double2(tt, td);   // c_e and d_e = Dinv_e rhs_e (for both sweep directions)
+            rec_other[(size_t)chain_loc<B>(S_, -dir, i, j) * REC + ChainCfg<B>::d_off(r)] = td;
         }
         __syncthreads();
     }
@@ -1002,18 +1007,6 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
         const unsigned band = item / tiles_band;
         const unsigned q0 = (item - band * tiles_band) * TE;              // first record of the tile inside the band
         const int cnt = (int)(per_band - q0 < (unsigned)TE ? per_band - q0 : (unsigned)TE);
-        {   // stage the tile (REC is even: 16-byte pieces), four loads in flight per thread
-            const double2 *src = reinterpret_cast<const double2 *>(rec + ((size_t)band * per_band + q0) * REC);
-            double2 *dst = reinterpret_cast<double2 *>(s_rec);
-            const int n2 = cnt * (REC / 2);
-            int t = threadIdx.x;
-            for (; t + 3 * NT < n2; t += 4 * NT) {
-                const double2 v0 = __ldcs(src + t), v1 = __ldcs(src + t + NT), v2 = __ldcs(src + t + 2 * NT),
-                              v3 = __ldcs(src + t + 3 * NT);
-                dst[t] = v0; dst[t + NT] = v1; dst[t + 2 * NT] = v2; dst[t + 3 * NT] = v3;
-            }
-            for (; t < n2; t += NT) dst[t] = __ldcs(src + t);
-        }
         long long e = -1;
         int i = 0, j = 0;
         if (el < cnt) {
@@ -1026,6 +1019,26 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
                 e = (long long)j * Ni + i;
             }
         }
+        // my row of the diagonal block: requested now, used after the second barrier
+        double av[B];
+        if (e >= 0) {
+            int c5[5], rk[5];
+            S_.cols(i, j, c5);
+            slot_ranks(c5, rk);
+            load_row<B>(data + ((size_t)(S_.row_start(i, j) + rk[0]) * B + r) * B, av);
+        }
+        {   // stage the tile (REC is even: 16-byte pieces), four loads in flight per thread
+            const double2 *src = reinterpret_cast<const double2 *>(rec + ((size_t)band * per_band + q0) * REC);
+            double2 *dst = reinterpret_cast<double2 *>(s_rec);
+            const int n2 = cnt * (REC / 2);
+            int t = threadIdx.x;
+            for (; t + 3 * NT < n2; t += 4 * NT) {
+                const double2 v0 = __ldcs(src + t), v1 = __ldcs(src + t + NT), v2 = __ldcs(src + t + 2 * NT),
+                              v3 = __ldcs(src + t + 3 * NT);
+                dst[t] = v0; dst[t + NT] = v1; dst[t + 2 * NT] = v2; dst[t + 3 * NT] = v3;
+            }
+            for (; t < n2; t += NT) dst[t] = __ldcs(src + t);
+        }
         if (e >= 0) {
             const bool has_row = (i - dirp >= 0 && i - dirp < Ni), has_up = S_.active(j - dirp);
             s_x[el * B + r] = x[e * B + r];
@@ -1036,7 +1049,7 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
         if (e >= 0) {
             const double *m = s_rec + (size_t)el * REC;
             const double *xr = s_x + (TE + el) * B, *xu = s_x + (2 * TE + el) * B;
-            double a0 = m[2 * B2 + r] - s_x[el * B + r], a1 = 0.0;
+            double a0 = m[C::c_off(r)] - s_x[el * B + r], a1 = 0.0;
 #pragma unroll
             for (int c = 0; c < B; ++c) {
                 a0 = fma(m[C::mat_offset(r, c)], xr[c], a0);
@@ -1052,11 +1065,9 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
         __syncthreads();
         if (e >= 0) {
             // the diagonal block of row e sits at row_start + (number of smaller columns)
-            int c5[5], rk[5];
-            S_.cols(i, j, c5);
-            slot_ranks(c5, rk);
-            const double *d = data + ((size_t)(S_.row_start(i, j) + rk[0]) * B + r) * B;
-            const double res = row_dot<B>(d, s_rho + el * B);
+            double res = 0.0;
+#pragma unroll
+            for (int c = 0; c < B; ++c) res = fma(av[c], s_rho[el * B + c], res);
             if (r_out != nullptr) r_out[e * B + r] = res;
             sumsq = fma(res, res, sumsq);
         }
@@ -1106,7 +1117,7 @@ k_gs_edge_helper(const double *__restrict__ data, const int32_t *__restrict__ in
 #pragma unroll
             for (int c = 0; c < B; ++c) tt = fma(d[c], s_t[el * B + c], tt);
             const int j = e / Ni, i = e - j * Ni;
-            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + 2 * B2 + r;
+            double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + ChainCfg<B>::c_off(r);
             if (S_.ja1 - S_.ja0 == 1 && nlo && nhi) atomicAdd(mine, -tt);   // both ghost terms land on one entry
             else *mine -= tt;
         }
@@ -1366,7 +1377,8 @@ static int helper_residual_t(const dgb_operator *op, const double *rhs, const do
     double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
-    if (grid > sm_count() * 6) grid = sm_count() * 6;       // one wave at the occupancy __launch_bounds__ asks for
+    constexpr int occ = (B > 4 && B <= 16) ? 5 : 6;
+    if (grid > sm_count() * occ) grid = sm_count() * occ;    // one wave at the occupancy __launch_bounds__ asks for
     if (grid > kMaxPartials) grid = kMaxPartials;
     k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
                                                  dir, nullptr, r, partials, x_zero ? 1 : 0);

@@ -117,6 +117,35 @@ __device__ __forceinline__ double row_dot(const double *__restrict__ a, const do
     return t;
 }
 
+// a row of B doubles into registers with aligned 16-byte loads (same window trick as row_dot: an odd-b row that starts
+// at 8 mod 16 is read from one double earlier, the stray entries are dropped)
+template <int B>
+__device__ __forceinline__ void load_row(const double *__restrict__ a, double (&v)[B]) {
+    if (B == 1) {
+        v[0] = a[0];
+    } else if (B % 2 == 0) {
+        const double2 *a2 = reinterpret_cast<const double2 *>(a);
+#pragma unroll
+        for (int k = 0; k < B / 2; ++k) {
+            const double2 t = a2[k];
+            v[2 * k] = t.x;
+            v[2 * k + 1] = t.y;
+        }
+    } else {
+        const int mis = (int)((reinterpret_cast<uintptr_t>(a) >> 3) & 1);
+        const double2 *a2 = reinterpret_cast<const double2 *>(a - mis);
+        double w[B + 1];
+#pragma unroll
+        for (int k = 0; k < (B + 1) / 2; ++k) {
+            const double2 t = a2[k];
+            w[2 * k] = t.x;
+            w[2 * k + 1] = t.y;
+        }
+#pragma unroll
+        for (int c = 0; c < B; ++c) v[c] = mis ? w[c + 1] : w[c];
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,6 +36,7 @@ class Solver:
         self.residuals = []
         self._hier = None
         self.timings = {}
+        self.graph_launches = self.graph_replays = 0
 
     # ------------------------------------------------------------------------------------
     def solve(self):
@@ -174,12 +175,43 @@ class Solver:
             self._build_hierarchy()
         return self._hier
 
-    def _vcycle_device(self, k):
-        H = self.hierarchy()
-        L = _lib.load()
-        rc = L.dgb_vcycle(H["levels"], k, ctypes.byref(H["opts"]), H["ctl"].data_ptr(), H["partials"].data_ptr(),
-                          H["sumsq"].data_ptr(), _lib.stream_ptr())
+    def _launch_vcycle(self, H, k):
+        rc = _lib.load().dgb_vcycle(H["levels"], k, ctypes.byref(H["opts"]), H["ctl"].data_ptr(),
+                                    H["partials"].data_ptr(), H["sumsq"].data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "dgb_vcycle")
+
+    def _vcycle_device(self, k):
+        """One V-cycle (dgb_vcycle).  The launch sequence of a full cycle is fixed (the smoother's early exit is a
+        device-side flag), so from the third call on it is replayed as one CUDA graph: the ~150 kernels of the
+        coarse levels are shorter than their launch latency otherwise (`solver.b200.cuda graph: False` or
+        DGB_VCYCLE_GRAPH=0 keeps plain launches)."""
+        H = self.hierarchy()
+        use_graph = k == H["n"] and not H["opts"].u_final_event and H.get("graph_ok", True) and \
+            os.environ.get("DGB_VCYCLE_GRAPH", "1") != "0" and self.settings.get("solver.b200.cuda_graph", True)
+        if not use_graph:
+            return self._launch_vcycle(H, k)
+        if H.get("graph") is not None:
+            H["graph"].replay()
+            self.graph_replays += 1
+            return
+        H["vcalls"] = H.get("vcalls", 0) + 1
+        if H["vcalls"] < 3:
+            return self._launch_vcycle(H, k)
+        torch = _lib.require_cuda()
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = _lib.load().dgb_launch_count(0)
+            with torch.cuda.graph(g):
+                self._launch_vcycle(H, k)
+            self.graph_launches = int(_lib.load().dgb_launch_count(0) - before)      # kernels one replay launches
+            H["graph"] = g
+        except Exception:                    # capture is an optimisation: fall back to plain launches
+            H["graph_ok"] = False
+            torch.cuda.synchronize()
+            return self._launch_vcycle(H, k)
+        H["graph"].replay()
+        self.graph_replays += 1
 
     def _check_divergence(self):
         """Host-side view of the device state, wherever the host synchronises anyway: the sticky `diverged`
