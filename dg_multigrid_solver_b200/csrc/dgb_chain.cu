@@ -324,6 +324,9 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
     return true;
 }
 
+#ifndef DGB_CHAIN_NOFENCE
+#define DGB_CHAIN_NOFENCE 0
+#endif
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const double *__restrict__ wrapm,
@@ -335,6 +338,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     constexpr uint32_t S = BP * 8;                 // bytes per ring slot
     constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NOFENCE = DGB_CHAIN_NOFENCE;
     if (skip != nullptr && *skip != 0) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_ticket;
@@ -642,7 +646,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
         }
         __syncwarp();
         if (lane == 0 && n + NS < nchunks) {
-            fence_proxy_async();
+            if (NOFENCE == 0) fence_proxy_async();
             issue(n + NS);
         }
     }
