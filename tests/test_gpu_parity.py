@@ -595,3 +595,27 @@ def test_stokes_global_order_and_distributive_gauss_seidel():
     assert len(hist) == len(ref) == 316                     # 315 outer iterations + the converged one
     assert np.allclose(hist, ref, rtol=1e-8, atol=1e-12)    # 315 accumulated iterations: 1.5e-10 already oracle vs reference
     assert rel_err(u, g["dgs_u_final"]) < 1e-10
+
+
+def test_cli_entry_points(tmp_path, monkeypatch):
+    """`python -m dg_multigrid_solver_b200 -m | -s --smoother X | -d` from a directory laid out like the reference's
+    (input/paramfile.yml + grid folder): the shipped paramfile as-is reproduces the reference's 8 V-cycles and error
+    norms, the smoother and direct runs reach the reference's residuals."""
+    import shutil
+    from helpers import REPO
+    from dg_multigrid_solver_b200.__main__ import main
+    (tmp_path / "input").mkdir()
+    shutil.copy(os.path.join(REPO, "input", "paramfile.yml"), tmp_path / "input" / "paramfile.yml")
+    shutil.copy(os.path.join(REPO, "input", "Rectangle_8X8_nPoly5.xyz"), tmp_path / "input" / "Rectangle_8X8_nPoly5.xyz")
+    monkeypatch.chdir(tmp_path)
+    g = golden("shipped")
+    d = main(["-m", "--silent"])
+    assert d is not None
+    assert len(d.solver.residuals) == len(g["residuals"]) == 9
+    assert np.allclose(d.solver.residuals, g["residuals"], rtol=HIST_RTOL, atol=HIST_ATOL)
+    assert abs(d.L2_error_u - float(g["L2_error"])) < 1e-9
+    assert os.path.exists(os.path.join(d.results_dir, "summary.txt"))
+    d = main(["-s", "--smoother", "block_gauss_seidel_pyamg", "--silent"])
+    assert d is not None and 0.0 < d.residual_normalized < 1.0
+    d = main(["-d", "--silent"])
+    assert d is not None and d.residual_normalized < 1e-11
