@@ -117,6 +117,7 @@ SIGNATURES = {
     "dgb_block_gs_entry_residual": (c_i32, [OP, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_block_gs_residual_after_pass": (c_i32, [OP, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dgb_block_gs_colour": (c_i32, [OP, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "dgb_block_gs_colour_entry": (c_i32, [OP, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "dgb_block_relax_sweep": (c_i32, [OP, c_vp, c_vp, c_vp, c_f64, c_vp]),
     "dgb_smoother_begin": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "dgb_smoother_check": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
@@ -159,6 +160,8 @@ def load(path=None):
         L.dgb_set_kernel_path(1)
     if os.environ.get("DGB_CHAIN_MASK"):        # tuning: block sizes of the chained Gauss-Seidel kernel
         L.dgb_set_kernel_path(300 + int(os.environ["DGB_CHAIN_MASK"]))
+    if os.environ.get("DGB_GS_VARIANT"):        # tuning: A/B switches of the smoother kernels (dgb_stream.cu)
+        L.dgb_set_kernel_path(100 + int(os.environ["DGB_GS_VARIANT"]))
     _lib = L
     return L
 

@@ -368,13 +368,19 @@ struct SlabCtx {
     dgb_smoother_ctl *ctl;
     double *partials, *sumsq;
     void *stream;
+    // level whose ghost rows are current (no owned row of it changed since its last exchange), -1 none: every rank
+    // takes the same decisions, so an exchange that would move the same bits again is dropped on all of them
+    mutable int halo_fresh = -1;
 };
 
 static int halo(const SlabCtx &s, int k) {
+    if (s.halo_fresh == k) return 0;
     const dgb_slab_level &L = s.lv[k];
     const int rows = L.lev.op.Nj - L.ghost_lo - L.ghost_hi;
+    s.halo_fresh = k;
     return dgb_halo_exchange(s.comm, L.u_block, (int64_t)L.lev.op.Ni * L.lev.op.b, rows, s.stream);
 }
+static void touched(const SlabCtx &s) { s.halo_fresh = -1; }
 
 // global sum of squares of rhs - A u over the owned rows -> *sumsq, then the residual test `mode` (0 none)
 // relaxed_colour >= 0: that colour was relaxed last and nothing changed since -- its rows are skipped
@@ -412,12 +418,14 @@ static int gs_pass(const SlabCtx &s, int k, int direction, int prev, const int32
             if (colour == *last_colour) continue;
             if ((rc = halo(s, k))) return rc;
             if ((rc = dgb_block_gs_colour(&L.lev.op, L.lev.rhs, L.lev.u, colour, L.colour_shift, skip, s.stream))) return rc;
+            touched(s);
             *last_colour = colour;
         }
         return 0;
     }
     // slab_lexicographic: lexicographic inside the slab, the neighbours' rows as they were before the pass
     if ((rc = halo(s, k))) return rc;
+    touched(s);
     return dgb_block_gs_pass_seq(&L.lev.op, L.lev.rhs, L.lev.u, direction, prev, skip, s.stream);
 }
 
@@ -437,15 +445,27 @@ static int smooth(const SlabCtx &s, int k, bool post, double *r_keep, bool *have
     const bool check = s.o->check_residual != 0;
     const int32_t *skip = nullptr;
     int prev = 0, rc;
+    int last_colour = -1;
     if (check) {
         const int first = direction >= 0 ? +1 : -1;
         bool fused = false;
         const bool lexi = s.o->gs_mode != DGB_GS_REDBLACK;
-        if ((rc = residual_test(s, k, r_keep, nullptr, 1, lexi ? first : 0, &fused))) return rc;
-        if (fused) prev = -first;
+        if (!lexi && L.lev.op.stencil >= 0) {
+            // 2-colour mode: the entry residual kernel also relaxes the first colour of the first pass
+            const int c0 = first > 0 ? 0 : 1;
+            if ((rc = halo(s, k))) return rc;
+            if ((rc = dgb_block_gs_colour_entry(&L.lev.op, L.lev.rhs, L.lev.u, r_keep, c0, L.colour_shift, s.partials, s.sumsq,
+                                                &s.ctl[k].diverged, s.stream)))
+                return rc;
+            touched(s);
+            if ((rc = dgb_allreduce_sum(s.comm, s.sumsq, 1, s.ctl + k, L.n_global, s.stream))) return rc;
+            last_colour = c0;
+        } else {
+            if ((rc = residual_test(s, k, r_keep, nullptr, 1, lexi ? first : 0, &fused))) return rc;
+            if (fused) prev = -first;
+        }
         skip = &s.ctl[k].skip;
     }
-    int last_colour = -1;
     for (int it = 0; it < iterations; ++it) {
         if (direction >= 0) {
             if ((rc = gs_pass(s, k, +1, prev, skip, &last_colour))) return rc;
@@ -476,10 +496,12 @@ static int vcycle_slab(const SlabCtx &s, int k) {
             return rc;
         // solver.py:171 -- the whole block (ghost rows included) starts from zero
         DGB_CUDA_OK(cudaMemsetAsync(C.u_block, 0, sizeof(double) * (size_t)c.op.Ni * c.op.b * (c.op.Nj - C.ghost_lo - C.ghost_hi + 2), st));
+        s.halo_fresh = k - 1;       // zero everywhere, the neighbours' rows included
         if ((rc = vcycle_slab(s, k - 1))) return rc;
         if ((rc = dgb_prolong_add_slab(c.transfer_kind, c.P, c.nc, c.nf, c.op.Ni, c.op.Nj, C.ghost_lo, C.ghost_hi, L.ghost_lo,
                                        c.u, L.lev.u, s.stream)))
             return rc;
+        touched(s);
     } else {
         // the link to the replicated hierarchy: restrict into an un-ghosted chunk, gather the chunks of all ranks on
         // every rank, run the rest of the cycle redundantly (identical bits everywhere), prolong my chunk back
@@ -496,6 +518,7 @@ static int vcycle_slab(const SlabCtx &s, int k) {
         if ((rc = dgb_prolong_add_slab(o.link_kind, o.link_P, o.link_nc, o.link_nf, o.link_Ni_c, o.link_rows_c, 0, 0, L.ghost_lo,
                                        top.u + (size_t)s.comm->rank * chunk, L.lev.u, s.stream)))
             return rc;
+        touched(s);
     }
     return smooth(s, k, true, nullptr, nullptr);
 }

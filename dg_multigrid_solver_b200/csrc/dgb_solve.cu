@@ -41,6 +41,7 @@ struct Sel {
     int i_lo;   // mode 2: first i on the diagonal
     int count;  // number of candidate items (mode 0/1: Ni*Nj, mode 2: elements on the diagonal)
     const int32_t *list;   // mode 4: explicit block-row list (one dependency level of a generic Gauss-Seidel pass)
+    int keep_partner;      // mode 3 residual: leave the residual rows of the other colour alone (default: written as zero)
 };
 
 __device__ __forceinline__ int sel_element(const Sel &s, int idx) {
@@ -67,7 +68,10 @@ __device__ __forceinline__ int sel_partner(const Sel &s, int idx) {
     return i < s.Ni ? j * s.Ni + i : -1;
 }
 
-enum { MODE_APPLY = 0, MODE_RESIDUAL = 1, MODE_RELAX = 2 };
+// MODE_RESIDUAL_RELAX: the entry residual of a 2-colour smoother call fused with the relaxation of its first colour --
+// a row of that colour reads only its own x and the other colour's, so the in-place update races with nothing and the
+// four neighbour blocks are read once for both (r -> r_out, x relaxed in place unless *skip)
+enum { MODE_APPLY = 0, MODE_RESIDUAL = 1, MODE_RELAX = 2, MODE_RESIDUAL_RELAX = 3 };
 
 template <int B>
 struct RowCfg {
@@ -104,12 +108,14 @@ __global__ void __launch_bounds__(RowCfg<B>::NT)
 k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
        const int32_t *__restrict__ indptr, const double *__restrict__ dinv,
        const double *__restrict__ rhs, const double *x_in, double *x_out, double *partials,
-       double omega, Sel sel, const int32_t *__restrict__ skip) {
+       double omega, Sel sel, const int32_t *__restrict__ skip, double *r_out = nullptr) {
     constexpr int EPB = RowCfg<B>::EPB;
     constexpr int NT = RowCfg<B>::NT;
     constexpr int LP = RowCfg<B>::LP;
-    if (skip != nullptr && *skip != 0) return;
-    __shared__ __align__(16) double s_rsum[MODE == MODE_RELAX ? EPB * B : 2];
+    constexpr bool RELAXES = MODE == MODE_RELAX || MODE == MODE_RESIDUAL_RELAX;
+    const bool frozen = skip != nullptr && *skip != 0;
+    if (frozen && MODE != MODE_RESIDUAL_RELAX) return;
+    __shared__ __align__(16) double s_rsum[RELAXES ? EPB * B : 2];
     __shared__ double s_red[32];
     const int rowid = threadIdx.x / LP, h = threadIdx.x - rowid * LP;
     const int el = rowid / B;
@@ -122,21 +128,25 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
         const int idx = tile * EPB + el;
         int e = -1;
         if (lane_ok && idx < sel.count) e = sel_element(sel, idx);
-        if (MODE == MODE_RESIDUAL && sel.mode == 3 && lane_ok && idx < sel.count && writer && x_out != nullptr) {
+        if (MODE == MODE_RESIDUAL && sel.mode == 3 && !sel.keep_partner && lane_ok && idx < sel.count && writer &&
+            x_out != nullptr) {
             const int ep = sel_partner(sel, idx);  // a row of the colour relaxed last: its residual is zero (to rounding)
             if (ep >= 0 && indptr[ep] != indptr[ep + 1]) x_out[(size_t)ep * B + r] = 0.0;
         }
-        double acc = 0.0;
+        double acc = 0.0, acc_diag = 0.0;
         if (e >= 0) {
             const int j0 = indptr[e], j1 = indptr[e + 1];
             if (j0 == j1) e = -1;        // empty block row (ghost row of a slab): not part of this rank's operator
             for (int jj = j0; jj < j1; ++jj) {
                 const int col = indices[jj];
                 if (MODE == MODE_RELAX && col == e) continue;
-                acc += row_dot_part<B, LP>(data + ((size_t)jj * B + r) * B, x_in + (size_t)col * B, h);
+                const double t = row_dot_part<B, LP>(data + ((size_t)jj * B + r) * B, x_in + (size_t)col * B, h);
+                if (MODE == MODE_RESIDUAL_RELAX && col == e) acc_diag = t;
+                else acc += t;
             }
         }
         if (LP == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);      // the two halves of the row
+        if (LP == 2 && MODE == MODE_RESIDUAL_RELAX) acc_diag += __shfl_xor_sync(0xffffffffu, acc_diag, 1);
         if (MODE == MODE_APPLY) {
             if (e >= 0 && writer) x_out[(size_t)e * B + r] = acc;
         } else if (MODE == MODE_RESIDUAL) {
@@ -146,19 +156,27 @@ k_rows(const double *__restrict__ data, const int32_t *__restrict__ indices,
                 sumsq = fma(res, res, sumsq);
             }
         } else {
-            if (e >= 0 && writer) s_rsum[el * B + r] = rhs[(size_t)e * B + r] - acc;
+            if (e >= 0 && writer) {
+                const double rest = rhs[(size_t)e * B + r] - acc;
+                s_rsum[el * B + r] = rest;
+                if (MODE == MODE_RESIDUAL_RELAX) {
+                    const double res = rest - acc_diag;
+                    if (r_out != nullptr) r_out[(size_t)e * B + r] = res;
+                    sumsq = fma(res, res, sumsq);
+                }
+            }
             __syncthreads();
             double t = 0.0;
             if (e >= 0) t = row_dot_part<B, LP>(dinv + ((size_t)e * B + r) * B, s_rsum + el * B, h);
             if (LP == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
-            if (e >= 0 && writer) {
+            if (e >= 0 && writer && !frozen) {
                 const double xo = x_in[(size_t)e * B + r];
                 x_out[(size_t)e * B + r] = (omega == 1.0) ? t : omega * t + (1.0 - omega) * xo;
             }
             __syncthreads();
         }
     }
-    if (MODE == MODE_RESIDUAL) {
+    if (MODE == MODE_RESIDUAL || MODE == MODE_RESIDUAL_RELAX) {
         const double t = block_sum<NT>(sumsq, s_red);
         if (threadIdx.x == 0) partials[blockIdx.x] = t;
     }
@@ -438,6 +456,8 @@ static int check_op(const dgb_operator *op) {
 extern "C" {
 int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const double *x, double *r, int32_t relaxed,
                             int32_t shift, double *partials, double *sumsq, const int32_t *skip, void *stream);
+int dgb_block_gs_colour_entry(const dgb_operator *op, const double *rhs, double *x, double *r, int32_t first,
+                              int32_t shift, double *partials, double *sumsq, const int32_t *frozen, void *stream);
 static int lexicographic_pass(const dgb_operator *op, const double *rhs, double *x, double omega, int direction,
                               const int32_t *skip, cudaStream_t st, bool have_c = false);
 }
@@ -457,6 +477,7 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
     const int64_t n = (int64_t)op->Ni * op->Nj * op->b;
     DGB_ARG(op->dinv && rhs && u);
     int last_dir = 0;      // direction of the previous lexicographic pass of this call (u untouched since)
+    int entry_colour = -1; // 2-colour mode: the colour the entry residual kernel already relaxed
     // every pass of this call runs in the chained kernel with the c-recurrence (no ghost rows): the records of the
     // opposite direction are complete after each pass
     const bool chained_loop = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
@@ -476,6 +497,11 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
             k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, nullptr);
             DGB_LAUNCH_OK();
             last_dir = -first_dir;          // the first pass finds its c in place
+        } else if (mode == DGB_GS_REDBLACK && max_iterations > 0 && op->stencil >= 0 && g_gs_variant != 43) {
+            // the first colour of the first pass is relaxed by the kernel that evaluates its entry residual
+            entry_colour = first_dir > 0 ? 0 : 1;
+            rc = dgb_block_gs_colour_entry(op, rhs, u, r_keep, entry_colour, 0, partials, sumsq, &ctl->diverged, stream);
+            if (rc) return rc;
         } else {
             rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, nullptr, stream);
             if (rc) return rc;
@@ -487,7 +513,7 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
     // 2-colour mode: relaxing a colour twice in a row with nothing in between recomputes the same values bit for bit
     // (x_e = Dinv_e (rhs_e - sum A x_other colour)), so the second of two adjacent passes over one colour is dropped:
     // a symmetric iteration 0,1 | 1,0 runs 0,1,0 and the next one starts at 1
-    int last_colour = -1;
+    int last_colour = entry_colour;
     for (int it = 0; it < max_iterations; ++it) {
         for (int dir = +1; dir >= -1; dir -= 2) {
             if ((dir > 0 && direction < 0) || (dir < 0 && direction > 0)) continue;
@@ -594,6 +620,32 @@ int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const dou
                        op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, sel, skip));
     DGB_LAUNCH_OK();
     k_sum_partials<<<1, 1024, 0, st>>>(partials, grid, sumsq, skip);
+    DGB_LAUNCH_OK();
+    return 0;
+}
+
+// Entry of a 2-colour smoother call: r = rhs - A x and its sum of squares over all rows, and colour `first` relaxed in
+// place.  Two launches: the rows of the other colour (residual only; they read the first colour's x, so they go
+// first), then the rows of `first` (residual + relaxation from one read of their blocks).
+int dgb_block_gs_colour_entry(const dgb_operator *op, const double *rhs, double *x, double *r, int32_t first,
+                              int32_t shift, double *partials, double *sumsq, const int32_t *frozen, void *stream) {
+    int rc = check_op(op);
+    if (rc) return rc;
+    DGB_ARG(op->dinv && x && rhs && partials && sumsq && (first == 0 || first == 1));
+    if (op->stencil < 0) return DGB_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    int g0 = 1, g1 = 1;
+    Sel other{3, 1 - first, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj, nullptr, 1};
+    Sel mine{3, first, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj, nullptr, 1};
+    DGB_DISPATCH_B_ANY(op->b, g0 = rows_grid(other.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
+                   k_rows<B, MODE_RESIDUAL><<<g0, RowCfg<B>::NT, 0, st>>>(
+                       op->data, op->indices, op->indptr, nullptr, rhs, x, r, partials, 1.0, other, nullptr));
+    DGB_LAUNCH_OK();
+    DGB_DISPATCH_B_ANY(op->b, g1 = rows_grid(mine.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL_RELAX>());
+                   k_rows<B, MODE_RESIDUAL_RELAX><<<g1, RowCfg<B>::NT, 0, st>>>(
+                       op->data, op->indices, op->indptr, op->dinv, rhs, x, x, partials + g0, 1.0, mine, frozen, r));
+    DGB_LAUNCH_OK();
+    k_sum_partials<<<1, 1024, 0, st>>>(partials, g0 + g1, sumsq, nullptr);
     DGB_LAUNCH_OK();
     return 0;
 }

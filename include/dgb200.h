@@ -222,6 +222,14 @@ int dgb_block_gs_residual_after_pass(const dgb_operator *h_op, const double *x, 
 int dgb_block_gs_colour(const dgb_operator *h_op, const double *rhs, double *x, int32_t colour, int32_t shift,
                         const int32_t *skip, void *stream);
 
+/* Entry of a 2-colour smoother call (the residual before the first iteration, dgfem/relaxation.py:202-204, together
+ * with the first colour of the first pass): r = rhs - A x over all rows (r may be NULL), *sumsq = sum r^2, and the
+ * rows of colour `first` relaxed in place unless *frozen (device flag, may be NULL) is set.  The rows of `first`
+ * read their four neighbour blocks once for both results (5.5 b^2 doubles per element instead of 7.5).  Needs the DG
+ * stencil layout (stencil >= 0), otherwise DGB_UNSUPPORTED and nothing is launched. */
+int dgb_block_gs_colour_entry(const dgb_operator *h_op, const double *rhs, double *x, double *r, int32_t first,
+                              int32_t shift, double *partials, double *sumsq, const int32_t *frozen, void *stream);
+
 /* ---- K8: one block-row relaxation sweep, x_out_i = omega*Dinv_i(rhs_i - sum_{j!=i} A_ij x_in_j)
  *                                                   + (1-omega) x_in_i
  * x_out != x_in : block-Jacobi            (first iteration of dgfem/relaxation.py:123-150)

@@ -219,6 +219,45 @@ def test_redblack_mode_matches_its_oracle():
     assert np.allclose(d.solver.residuals, hist, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["c1", "circ8_h24", "shipped"])
+def test_colour_entry_is_residual_plus_first_colour(name):
+    """dgb_block_gs_colour_entry == dgb_bsr_residual followed by dgb_block_gs_colour(first), on every level
+    (b = 4, 9, 16, 36; Dirichlet and O-grid), either first colour, either row parity, with and without the freeze flag."""
+    import torch
+    from dg_multigrid_solver_b200 import _lib
+    d = build(CASES[name])
+    L = _lib.load()
+    st = _lib.stream_ptr()
+    rng = np.random.default_rng(5)
+    part = torch.zeros(L.dgb_partials_len(), dtype=torch.float64, device="cuda")
+    for grid in d.grids:
+        op = grid.operator()
+        n = grid.d_rhs.numel()
+        x0 = torch.from_numpy(rng.standard_normal(n)).cuda()
+        for first in (0, 1):
+            for shift in (0, 1):
+                ss_ref = torch.zeros(1, dtype=torch.float64, device="cuda")
+                r_ref = torch.empty_like(x0)
+                x_ref = x0.clone()
+                _lib.call("dgb_bsr_residual", op, grid.d_rhs, x_ref, r_ref, part, ss_ref, None, st)
+                _lib.call("dgb_block_gs_colour", op, grid.d_rhs, x_ref, first, shift, None, st)
+                for frozen in (None, 0, 1):
+                    flag = None if frozen is None else torch.full((1,), frozen, dtype=torch.int32, device="cuda")
+                    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+                    r = torch.full_like(x0, float("nan"))
+                    x = x0.clone()
+                    _lib.call("dgb_block_gs_colour_entry", op, grid.d_rhs, x, r, first, shift, part, ss, flag, st)
+                    assert float((r - r_ref).abs().max()) <= 1e-13 * float(r_ref.abs().max()), (name, grid.Ni, grid.b)
+                    assert abs(float(ss.item()) - float(ss_ref.item())) <= 1e-13 * float(ss_ref.item())
+                    assert torch.equal(x, x0 if frozen == 1 else x_ref), (name, grid.Ni, grid.b, first, shift, frozen)
+                x = x0.clone()                                        # r is optional
+                ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+                _lib.call("dgb_block_gs_colour_entry", op, grid.d_rhs, x, None, first, shift, part, ss, None, st)
+                assert torch.equal(x, x_ref)
+                assert abs(float(ss.item()) - float(ss_ref.item())) <= 1e-13 * float(ss_ref.item())
+    assert L.dgb_device_error(1) == 0
+
+
 def _synthetic(kind, Ni, Nj, P):
     from dgoracle import plot3d
     return plot3d.rectangle_nodes(Ni, Nj, P) if kind == "rect" else plot3d.circle_in_circle_nodes(Ni, Nj, P)
