@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgb200.so")
+LIB_PATH = os.environ.get("DGB_LIB", os.path.join(_HERE, "libdgb200.so"))      # DGB_LIB: a diagnostic build
 _lib = None
 
 c_i32, c_i64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p

@@ -35,14 +35,17 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    # DGB_NVCC_EXTRA / DGB_LIB_OUT: diagnostic builds next to the product library (e.g. -DDGB_CHAIN_TRACE)
+    extra = os.environ.get("DGB_NVCC_EXTRA", "").split()
+    out = os.environ.get("DGB_LIB_OUT", LIB)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libdgb200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

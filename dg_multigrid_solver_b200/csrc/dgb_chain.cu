@@ -25,6 +25,8 @@
 // element across the wrap; its pre-multiplied block lives in a small side array (one per row and direction) and
 // is staged in shared memory and applied by the fill/drain path of the chain kernel.  Grids periodic in j keep the
 // row-pipelined kernel.
+#include <stdlib.h>
+
 #include "dgb_async.cuh"
 #include "dgb_common.cuh"
 #include "dgb_mma.cuh"
@@ -327,6 +329,19 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
 #ifndef DGB_CHAIN_NOFENCE
 #define DGB_CHAIN_NOFENCE 0
 #endif
+// -DDGB_CHAIN_TRACE: diagnostic build (tools/gpu/r02_chain_trace.sh) -- every band records when it started, got its
+// first records, finished, and how long it sat in each kind of wait (8 x int64 per band, read by dgb_debug_chain_trace)
+#ifdef DGB_CHAIN_TRACE
+__device__ long long g_chain_trace[8 * 8192];
+__device__ __forceinline__ long long trace_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DGB_TRACE(x) x
+#else
+#define DGB_TRACE(x)
+#endif
 template <int B, int W, int DIR>
 __global__ void __launch_bounds__(W * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const double *__restrict__ wrapm,
@@ -371,6 +386,8 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     const int band = (ticket * (int)csize + (int)crank) * W + w;
     const int sr0 = band * R;                      // first row of the band, in sweep order
     if (sr0 >= nrows) return;
+    DGB_TRACE(long long tr_wait_up = 0; long long tr_n_wait = 0; long long tr_mbar = 0; long long tr_flow = 0;)
+    DGB_TRACE(if (lane == 0 && band < 8192) g_chain_trace[8 * band] = trace_now();)
     const int Rv = min(R, nrows - sr0);            // rows of this band
     uint64_t *full = bars + w * NS;
     // lane -> (element row g of the band, scalar row r, column part): lanes beyond the band's rows shadow row 0
@@ -504,7 +521,10 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     for (int n = 0; n < nchunks; ++n) {
         const int s = n % NS;
         const int t0 = n * CH;
+        DGB_TRACE(long long tr0 = clock64();)
         if (!mbar_wait(&full[s], (uint32_t)((n / NS) & 1), err)) return;
+        DGB_TRACE(if (n > 0) tr_mbar += clock64() - tr0; else if (lane == 0 && band < 8192) g_chain_trace[8 * band + 1] = trace_now();)
+        DGB_TRACE(tr0 = clock64();)
         // ---- once per chunk: flow control and the global hand-overs ----
         if (pred == 1 && lane == 0) s_prog[w] = t0;                           // columns < t0 are consumed
         if (succ == 1 || succ == 3) {
@@ -525,6 +545,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
             }
             __syncwarp();
         }
+        DGB_TRACE(tr_flow += clock64() - tr0;)
         const uint32_t si0 = (uint32_t)(t0 % RING) * S;                       // incoming-ring slot of column t0
         const uint32_t sr0b = (uint32_t)(t0 % RINGR) * S;                     // row-ring slot of step t0 (0 if RINGR == CH)
         uint32_t sm = rec_m + (uint32_t)s * (CH * KS), sc = rec_c + (uint32_t)s * (CH * KS);
@@ -574,7 +595,9 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
                 for (int c = 0; c < (P == 1 ? B : VN); ++c) mxh = max(mxh, (unsigned)__double2hiint(u[c]));
                 const bool wait_up = __any_sync(FULL, mxh == 0xffffffffu);
                 if (__builtin_expect(wait_up, 0)) {
+                    DGB_TRACE(const long long tw = clock64();)
                     if (!chain_wait_up<B>(uk, err)) return;
+                    DGB_TRACE(tr_wait_up += clock64() - tw; tr_n_wait += 1;)
                     chain_load_vec<B>(uk + po, u, nullptr);
                     xnew = row.eval(p, u);
                 }
@@ -650,6 +673,19 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
             issue(n + NS);
         }
     }
+#ifdef DGB_CHAIN_TRACE
+    if (lane == 0 && band < 8192) {
+        long long *tr = g_chain_trace + 8 * band;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[2] = trace_now();
+        tr[3] = tr_n_wait;
+        tr[4] = tr_wait_up;
+        tr[5] = tr_mbar;
+        tr[6] = tr_flow;
+        tr[7] = (long long)smid | ((long long)pred << 16) | ((long long)succ << 20) | ((long long)w << 24) | ((long long)crank << 32);
+    }
+#endif
 }
 
 
@@ -1274,19 +1310,20 @@ static long long chain_dir_len(int b, const Stencil &S_) {
     return 0;
 }
 
-int g_chain_cluster = 8;        // CTAs per cluster of the chain kernel (tuning: dgb_set_kernel_path(400 + n))
+int g_chain_cluster = 0;        // CTAs per cluster of the chain kernel, 0 = automatic (tuning: dgb_set_kernel_path(400 + n))
 
 template <int B, int W, int DIR>
 static int chain_launch_d(const double *rec, double *rec_other, const double *wrapm, double *x, double *mbox,
                           Stencil S_, const int32_t *skip, cudaStream_t st) {
     using C = ChainCfg<B>;
     static bool configured = false;
-    static int max_cluster = 1;
+    static int active[17] = {0};     // clusters of each size the device keeps resident at once
     auto kern = k_gs_chain<B, W, DIR>;
     if (!configured) {
         DGB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(W)));
-        // largest cluster size (<= 8, the portable limit) the device can co-schedule with this much shared memory
-        for (int cs = 8; cs >= 1; cs >>= 1) {
+        (void)cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);    // sizes 9..16
+        (void)cudaGetLastError();
+        for (int cs = 16; cs >= 1; --cs) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cs, 1, 1);
             cfg.blockDim = dim3(W * 32, 1, 1);
@@ -1299,19 +1336,37 @@ static int chain_launch_d(const double *rec, double *rec_other, const double *wr
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) {
-                max_cluster = cs;
-                break;
-            }
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) active[cs] = n;
             (void)cudaGetLastError();
         }
+        active[1] = active[1] > 0 ? active[1] : 1;
         configured = true;
+        if (getenv("DGB_CHAIN_VERBOSE"))
+            fprintf(stderr, "k_gs_chain<%d,%d>: resident clusters by size 1..16: %d %d %d %d %d %d %d %d | %d %d %d %d %d %d %d %d\n",
+                    B, W, active[1], active[2], active[3], active[4], active[5], active[6], active[7], active[8], active[9],
+                    active[10], active[11], active[12], active[13], active[14], active[15], active[16]);
     }
     DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
     const int nbands = (S_.ja1 - S_.ja0 + C::R - 1) / C::R;
     const int nctas = (nbands + W - 1) / W;
-    int cs = 1;
-    while (cs * 2 <= max_cluster && cs * 2 <= g_chain_cluster && cs < nctas) cs *= 2;
+    // Cluster size.  A level whose CTAs are all resident at once takes the portable maximum (8: fewest hand-overs
+    // through the global mailbox).  A larger level runs in waves -- a band starts when an earlier one has finished
+    // its whole row -- so what counts is how many CTAs the device keeps resident: size 8 fits 15 clusters (120 of 148
+    // SMs) on B200, size 9 also 15 (135 SMs), size 6 22 (132); measured on 2048^2 b = 9: 1.75 / 1.58 / 1.61 ms per pass
+    // (profiles/r02_probe_chain_cluster.md).  g_chain_cluster > 0 forces a size (tuning).
+    int cs = 8;
+    if (g_chain_cluster > 0) {
+        cs = g_chain_cluster < 16 ? g_chain_cluster : 16;
+    } else if (nctas > active[8] * 8) {
+        int best = active[8] * 8;
+        for (int c = 6; c <= 16; ++c)
+            if (active[c] * c > best || (active[c] * c == best && c > cs)) {
+                best = active[c] * c;
+                cs = c;
+            }
+    }
+    if (cs > nctas) cs = nctas;
+    while (cs > 1 && active[cs] == 0) --cs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(((nctas + cs - 1) / cs) * cs), 1, 1);
     cfg.blockDim = dim3(W * 32, 1, 1);
@@ -1478,7 +1533,8 @@ static int big_launch_d(const double *rec, double *rec_other, const double *wrap
     DGB_CUDA_OK(cudaMemsetAsync(work_ptr(), 0, sizeof(int), st));
     const int nctas = (S_.ja1 - S_.ja0 + W - 1) / W;
     int cs = 1;
-    while (cs * 2 <= max_cluster && cs * 2 <= g_chain_cluster && cs < nctas) cs *= 2;
+    const int cs_max = g_chain_cluster > 0 ? g_chain_cluster : 8;
+    while (cs * 2 <= max_cluster && cs * 2 <= cs_max && cs < nctas) cs *= 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(((nctas + cs - 1) / cs) * cs), 1, 1);
     cfg.blockDim = dim3(W * 32, 1, 1);
@@ -1586,3 +1642,10 @@ int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
 }
 
 }  // extern "C"
+
+#ifdef DGB_CHAIN_TRACE
+extern "C" int dgb_debug_chain_trace(long long *host_out, int n_bands) {
+    if (n_bands > 8192) n_bands = 8192;
+    return (int)cudaMemcpyFromSymbol(host_out, dgb::g_chain_trace, sizeof(long long) * 8 * n_bands);
+}
+#endif

@@ -808,7 +808,7 @@ int dgb_set_kernel_path(int32_t path) {
     if (path == 0 || path == 1) g_kernel_path = path;
     if (path >= 100 && path < 200) g_gs_variant = path - 100;      // tuning experiments only
     if (path >= 300 && path < 332) g_chain_mask = path - 300;      // block sizes of the chained GS kernel
-    if (path >= 400 && path <= 408) g_chain_cluster = path - 400;  // CTAs per cluster of the chained GS kernel
+    if (path >= 400 && path <= 416) g_chain_cluster = path - 400;  // CTAs per cluster of the chained GS kernel
     return old;
 }
 
