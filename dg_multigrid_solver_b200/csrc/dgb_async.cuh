@@ -38,6 +38,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe: the result arrives ~150 cycles later, nothing waits for it until it is used
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // returns false on timeout (and records it in *err)
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err) {
     for (int spin = 0; spin < kSpinLimit; ++spin) {

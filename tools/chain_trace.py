@@ -49,7 +49,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    out = np.zeros((min(nb, 8192), 8), dtype=np.int64)
+    out = np.zeros((min(nb, 8192), 12), dtype=np.int64)
     L.dgb_debug_chain_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     rc = L.dgb_debug_chain_trace(out.ctypes.data, out.shape[0])
     assert rc == 0, rc
@@ -77,6 +77,10 @@ def main():
         if m.any():
             res[f"lag_end_us[{k}]"] = {"n": int(m.sum()), "median": float(np.median(lag_end[m])), "mean": float(lag_end[m].mean())}
             res[f"lag_first_us[{k}]"] = {"median": float(np.median(lag_first[m])), "mean": float(lag_first[m].mean())}
+    nch = np.maximum(out[:, 10], 1)
+    res["cycles_per_chunk"] = {"mbar_wait": float(np.median(cyc_mbar / nch)), "flow_control": float(np.median(cyc_flow / nch)),
+                               "steps": float(np.median(out[:, 8] / nch)), "epilogue": float(np.median(out[:, 9] / nch)),
+                               "wait_up": float(np.median(cyc_wait / nch)), "band0": [float(out[0, k] / nch[0]) for k in (5, 6, 8, 9, 4)]}
     res["sum_lag_end_us"] = {k: float(lag_end[kind == k].sum()) for k in ("ring", "dsmem", "mailbox")}
     # when do bands start relative to their predecessor's end (a band that starts after its SM freed up)
     res["bands_started_after_t0_us"] = [float(v) for v in np.percentile(start, [0, 25, 50, 75, 100])]
