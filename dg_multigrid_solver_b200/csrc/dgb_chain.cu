@@ -39,6 +39,13 @@ int *err_ptr();
 extern int g_kernel_path;
 extern int g_gs_variant;
 
+// -DDGB_CHAIN_PRODUCER=0/1: force the refill scheme of every block size (default: ChainCfg<B>::PW)
+#ifdef DGB_CHAIN_PRODUCER
+#define DGB_CHAIN_PW(B) (DGB_CHAIN_PRODUCER)
+#else
+#define DGB_CHAIN_PW(B) ((B) <= 4 ? 1 : 0)
+#endif
+
 template <int B>
 struct ChainCfg {
     static constexpr int B2 = B * B;
@@ -68,6 +75,11 @@ struct ChainCfg {
     static constexpr int PCH = 8;                                     // mailbox columns per poll (multiple of CH)
     static constexpr int PSL = (PCH * B + 31) / 32;                   // mailbox doubles per lane and poll
     static constexpr int WDEF = B == 9 ? 8 : B == 16 ? 5 : B <= 4 ? 3 : 4;   // warps (bands) per CTA (shared memory bound)
+    // producer warp: one more warp per CTA refills the record stages of the W band warps (lane w serves warp w); a band
+    // warp then only arrives on its stage's "empty" mbarrier -- the proxy fence, expect_tx and bulk copy leave its
+    // critical path.  b = 4: pass -5.8 %; b = 9 (8 band warps per SM, two stages): +3 %, so it keeps refilling itself
+    // (profiles/r02_probe_chain_variants.md)
+    static constexpr int PW = DGB_CHAIN_PW(B);
     // doubles per row ring, padded so that the rows of a warp fall into different shared-memory banks
     static constexpr int RRS = RINGR * BP + (((RINGR * BP * 8) % 128) == 0 ? 4 : ((RINGR * BP * 8) % 128) == 64 ? 2 : 0);
     // O-grids: per warp, the wrap blocks of its R rows (staged once) and the rows' first new values
@@ -79,7 +91,7 @@ struct ChainCfg {
     // warp w: incoming ring at w * WR, then its R row rings; the CTA's outgoing ring is "warp W"'s incoming ring
     __host__ __device__ static constexpr size_t o_scr(int W) { return o_ring(W) + sizeof(double) * (W + 1) * WR; }
     __host__ __device__ static constexpr size_t o_bar(int W) { return o_scr(W) + sizeof(double) * SCR; }
-    __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * W * NS; }
+    __host__ __device__ static constexpr size_t o_prog(int W) { return o_bar(W) + sizeof(uint64_t) * 2 * W * NS; }   // full + empty
     __host__ __device__ static constexpr size_t o_wrap(int W) { return (o_prog(W) + sizeof(int) * (W + 1) + 15) & ~(size_t)15; }
     __host__ __device__ static constexpr size_t smem(int W) { return o_wrap(W) + sizeof(double) * W * WRAPD; }
 };
@@ -330,6 +342,7 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
 #define DGB_CHAIN_NOFENCE 0
 #endif
 
+
 // -DDGB_CHAIN_TRACE: diagnostic build (tools/gpu/r02_chain_trace.sh) -- every band records when it started, got its
 // first records, finished, and how long it sat in each kind of wait (12 x int64 per band, read by dgb_debug_chain_trace)
 #ifdef DGB_CHAIN_TRACE
@@ -344,7 +357,7 @@ __device__ __forceinline__ long long trace_now() {
 #define DGB_TRACE(x)
 #endif
 template <int B, int W, int DIR>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__((W + ChainCfg<B>::PW) * 32)
 k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const double *__restrict__ wrapm,
            double *__restrict__ x, double *mbox, Stencil S_, int *work, int *err, const int32_t *__restrict__ skip) {
     using C = ChainCfg<B>;
@@ -355,6 +368,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     constexpr uint32_t KS = R * REC * 8;           // bytes per step within a stage
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int NOFENCE = DGB_CHAIN_NOFENCE;
+    constexpr int PW = C::PW, NTH = (W + PW) * 32;
     if (skip != nullptr && *skip != 0) return;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_ticket;
@@ -370,10 +384,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     if (crank == 0 && threadIdx.x == 0) s_ticket = atomicAdd(&work[0], 1);
     if (threadIdx.x <= W) s_prog[threadIdx.x] = 0;
     // incoming rings start empty (all sentinel), row rings start at zero (the value "before" column 0)
-    for (int q = threadIdx.x; q < (W + 1) * WR; q += W * 32) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
-    if ((threadIdx.x & 31) == 0) {
+    for (int q = threadIdx.x; q < (W + 1) * WR; q += NTH) rings[q] = (q % WR) < RING * BP ? sentinel : 0.0;
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < W * 32) {
         uint64_t *bw = bars + (threadIdx.x >> 5) * NS;
-        for (int s = 0; s < NS; ++s) mbar_init(&bw[s], 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&bw[s], 1);
+            mbar_init(&bw[W * NS + s], 1);         // "stage consumed" (producer warp build)
+        }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -384,6 +401,40 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     asm volatile("" : "+r"(w));
     asm volatile("" : "+r"(lane));
     const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
+    if (PW && w == W) {
+        // ---- producer warp: lane cw refills the stages of band warp cw as they are handed back ----
+        const int cband = (ticket * (int)csize + (int)crank) * W + lane;
+        const int csr0 = cband * R;
+        int cn = NS, cchunks = 0;                   // next chunk to bring in (the first NS are issued by the band warp)
+        int cT = 0;
+        if (lane < W && csr0 < nrows) {
+            cT = Ni + min(R, nrows - csr0) - 1;
+            cchunks = (cT + CH - 1) / CH;
+        }
+        const double *csrc = rec + (size_t)cband * (Ni + R - 1) * R * REC;
+        double *cstage = stages + (size_t)lane * (NS * R * CH * REC);
+        uint64_t *cfull = bars + (lane < W ? lane : 0) * NS, *cempty = cfull + W * NS;
+        int spin = 0;
+        while (__any_sync(FULL, cn < cchunks)) {
+            const int cs = cn % NS;
+            const bool ok = cn < cchunks && mbar_test_wait(&cempty[cs], (uint32_t)((cn / NS - 1) & 1));
+            if (ok) {
+                const uint32_t bytes = (uint32_t)min(CH, cT - cn * CH) * KS;
+                mbar_expect_tx(&cfull[cs], bytes);
+                bulk_g2s(cstage + (size_t)cs * (CH * R * REC), csrc + (size_t)cn * (CH * R * REC), bytes, &cfull[cs]);
+                ++cn;
+                spin = 0;
+            }
+            if (!__any_sync(FULL, ok)) {
+                __nanosleep(40);
+                if (++spin > kSpinLimit || ((spin & 1023) == 1023 && *(volatile int *)err != 0)) {
+                    if (lane == 0) atomicExch(err, 1);
+                    return;
+                }
+            }
+        }
+        return;
+    }
     const int band = (ticket * (int)csize + (int)crank) * W + w;
     const int sr0 = band * R;                      // first row of the band, in sweep order
     if (sr0 >= nrows) return;
@@ -677,8 +728,12 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
         }
         __syncwarp();
         if (lane == 0 && n + NS < nchunks) {
-            if (NOFENCE == 0) fence_proxy_async();
-            issue(n + NS);
+            if (PW) {
+                mbar_arrive(&full[W * NS + s]);        // the stage is free: the producer warp refills it
+            } else {
+                if (NOFENCE == 0) fence_proxy_async();
+                issue(n + NS);
+            }
         }
         DGB_TRACE(__syncwarp(); tr_epi += clock64() - tr0;)
     }
@@ -1338,7 +1393,7 @@ static int chain_launch_d(const double *rec, double *rec_other, const double *wr
         for (int cs = 16; cs >= 1; --cs) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cs, 1, 1);
-            cfg.blockDim = dim3(W * 32, 1, 1);
+            cfg.blockDim = dim3((W + C::PW) * 32, 1, 1);
             cfg.dynamicSmemBytes = C::smem(W);
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1381,7 +1436,7 @@ static int chain_launch_d(const double *rec, double *rec_other, const double *wr
     while (cs > 1 && active[cs] == 0) --cs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(((nctas + cs - 1) / cs) * cs), 1, 1);
-    cfg.blockDim = dim3(W * 32, 1, 1);
+    cfg.blockDim = dim3((W + C::PW) * 32, 1, 1);
     cfg.dynamicSmemBytes = C::smem(W);
     cfg.stream = st;
     cudaLaunchAttribute at[1];
