@@ -1085,22 +1085,28 @@ template <int B>
 struct ResRecCfg {
     static constexpr int TE = (256 / B) > 0 ? (256 / B) : 1;            // records per tile
     static constexpr int NT = ((TE * B + 31) / 32) * 32;
-    // staged records | rho | x of the element, of its row predecessor and of its up predecessor
-    static constexpr size_t smem = sizeof(double) * ((size_t)TE * ChainCfg<B>::REC + 4 * TE * B);
+    static constexpr int NBUF = 2;                                       // tiles in flight per CTA (bulk copies)
+    // staged records (NBUF tiles) | rho | x of the element, of its row predecessor and of its up predecessor | mbarriers
+    static constexpr size_t o_bar = sizeof(double) * ((size_t)NBUF * TE * ChainCfg<B>::REC + 4 * TE * B);
+    static constexpr size_t smem = o_bar + sizeof(uint64_t) * NBUF;
 };
 
+// The CTA's tiles arrive by TMA bulk copies (a tile = TE consecutive records = one contiguous piece of the stream),
+// two tiles ahead of the arithmetic: the stream never waits for the three phases of a tile (stage x | rho | A_ee rho).
 template <int B>
 __global__ void __launch_bounds__(ResRecCfg<B>::NT)
 k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm, const double *__restrict__ data,
                const double *__restrict__ x, Stencil S_, int dirp /* direction of the records = -D */,
-               const int32_t *__restrict__ skip, double *r_out, double *partials) {
+               const int32_t *__restrict__ skip, double *r_out, double *partials, int *err) {
     using C = ChainCfg<B>;
-    constexpr int TE = ResRecCfg<B>::TE, NT = ResRecCfg<B>::NT, REC = C::REC, R = C::R, B2 = B * B;
+    using RC = ResRecCfg<B>;
+    constexpr int TE = RC::TE, NT = RC::NT, REC = C::REC, R = C::R, B2 = B * B, NBUF = RC::NBUF;
     if (skip != nullptr && *skip != 0) return;
-    extern __shared__ __align__(16) double s_dyn[];
-    double *s_rec = s_dyn;                       // [TE][REC]
-    double *s_rho = s_dyn + (size_t)TE * REC;    // [TE][B]
-    double *s_x = s_rho + TE * B;                // [3][TE][B]: x_e, x_row-pred, x_up-pred (zero when absent)
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    double *s_dyn = reinterpret_cast<double *>(s_raw);
+    double *s_rho = s_dyn + (size_t)NBUF * TE * REC;    // [TE][B]
+    double *s_x = s_rho + TE * B;                       // [3][TE][B]: x_e, x_row-pred, x_up-pred (zero when absent)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_raw + RC::o_bar);
     __shared__ double s_red[32];
     const int Ni = S_.Ni, nrows = S_.ja1 - S_.ja0;
     // work item = (band, tile of TE consecutive records of that band): 32-bit index arithmetic
@@ -1109,8 +1115,28 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
     const unsigned nbands = (unsigned)((nrows + R - 1) / R);
     const unsigned nitems = nbands * tiles_band;
     const int el = threadIdx.x / B, r = threadIdx.x - el * B;
+    // thread 0: bring the tile of work item `item` into buffer `buf`
+    auto fetch = [&](unsigned item, int buf) {
+        const unsigned band = item / tiles_band;
+        const unsigned q0 = (item - band * tiles_band) * TE;
+        const unsigned cnt = per_band - q0 < (unsigned)TE ? per_band - q0 : (unsigned)TE;
+        const uint32_t bytes = cnt * (uint32_t)(REC * sizeof(double));
+        mbar_expect_tx(&bars[buf], bytes);
+        bulk_g2s(s_dyn + (size_t)buf * TE * REC, rec + ((size_t)band * per_band + q0) * REC, bytes, &bars[buf]);
+    };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) mbar_init(&bars[b], 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int b = 0; b < NBUF; ++b)
+            if (blockIdx.x + (unsigned)b * gridDim.x < nitems) fetch(blockIdx.x + (unsigned)b * gridDim.x, b);
+    }
+    __syncthreads();
     double sumsq = 0.0;
-    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+    unsigned k = 0;
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x, ++k) {
+        const int buf = (int)(k % NBUF);
+        const double *s_rec = s_dyn + (size_t)buf * TE * REC;
         const unsigned band = item / tiles_band;
         const unsigned q0 = (item - band * tiles_band) * TE;              // first record of the tile inside the band
         const int cnt = (int)(per_band - q0 < (unsigned)TE ? per_band - q0 : (unsigned)TE);
@@ -1133,26 +1159,13 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
             S_.cols(i, j, c5);
             slot_ranks(c5, rk);
             load_row<B>(data + ((size_t)(S_.row_start(i, j) + rk[0]) * B + r) * B, av);
-        }
-        {   // stage the tile (REC is even: 16-byte pieces), four loads in flight per thread
-            const double2 *src = reinterpret_cast<const double2 *>(rec + ((size_t)band * per_band + q0) * REC);
-            double2 *dst = reinterpret_cast<double2 *>(s_rec);
-            const int n2 = cnt * (REC / 2);
-            int t = threadIdx.x;
-            for (; t + 3 * NT < n2; t += 4 * NT) {
-                const double2 v0 = __ldcs(src + t), v1 = __ldcs(src + t + NT), v2 = __ldcs(src + t + 2 * NT),
-                              v3 = __ldcs(src + t + 3 * NT);
-                dst[t] = v0; dst[t + NT] = v1; dst[t + 2 * NT] = v2; dst[t + 3 * NT] = v3;
-            }
-            for (; t < n2; t += NT) dst[t] = __ldcs(src + t);
-        }
-        if (e >= 0) {
             const bool has_row = (i - dirp >= 0 && i - dirp < Ni), has_up = S_.active(j - dirp);
             s_x[el * B + r] = x[e * B + r];
             s_x[(TE + el) * B + r] = has_row ? x[(e - dirp) * B + r] : 0.0;
             s_x[(2 * TE + el) * B + r] = has_up ? x[(e - (long long)dirp * Ni) * B + r] : 0.0;
         }
-        __syncthreads();
+        if (!mbar_wait(&bars[buf], (uint32_t)((k / NBUF) & 1), err)) return;
+        __syncthreads();          // s_x complete; everybody is done with the previous tile's rho
         if (e >= 0) {
             const double *m = s_rec + (size_t)el * REC;
             const double *xr = s_x + (TE + el) * B, *xu = s_x + (2 * TE + el) * B;
@@ -1169,7 +1182,8 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
             }
             s_rho[el * B + r] = a0 + a1;
         }
-        __syncthreads();
+        __syncthreads();          // rho complete; the tile's buffer and s_x are free
+        if (threadIdx.x == 0 && item + (unsigned)NBUF * gridDim.x < nitems) fetch(item + (unsigned)NBUF * gridDim.x, buf);
         if (e >= 0) {
             // the diagonal block of row e sits at row_start + (number of smaller columns)
             double res = 0.0;
@@ -1178,7 +1192,6 @@ k_residual_rec(const double *__restrict__ rec, const double *__restrict__ wrapm,
             if (r_out != nullptr) r_out[e * B + r] = res;
             sumsq = fma(res, res, sumsq);
         }
-        __syncthreads();
     }
     const double tsum = block_sum<NT>(sumsq, s_red);
     if (threadIdx.x == 0) partials[blockIdx.x] = tsum;
@@ -1536,7 +1549,7 @@ static int residual_rec_t(const dgb_operator *op, const double *x, int last_dir,
     long long grid = nbands * ((per_band + RC::TE - 1) / RC::TE);
     if (grid > (long long)sm_count() * occ) grid = (long long)sm_count() * occ;
     if (grid > kMaxPartials) grid = kMaxPartials;
-    k_residual_rec<B><<<(int)grid, RC::NT, RC::smem, st>>>(rec, wrapm, op->data, x, S_, dirp, skip, r, partials);
+    k_residual_rec<B><<<(int)grid, RC::NT, RC::smem, st>>>(rec, wrapm, op->data, x, S_, dirp, skip, r, partials, err_ptr());
     DGB_LAUNCH_OK();
     *grid_out = (int)grid;
     return 0;
