@@ -344,9 +344,9 @@ __device__ __noinline__ bool chain_wait_up(uint32_t uk, int *err) {
 
 
 // -DDGB_CHAIN_TRACE: diagnostic build (tools/gpu/r02_chain_trace.sh) -- every band records when it started, got its
-// first records, finished, and how long it sat in each kind of wait (12 x int64 per band, read by dgb_debug_chain_trace)
+// first records, finished, and how long it sat in each kind of wait (16 x int64 per band, read by dgb_debug_chain_trace)
 #ifdef DGB_CHAIN_TRACE
-__device__ long long g_chain_trace[12 * 8192];
+__device__ long long g_chain_trace[16 * 8192];
 __device__ __forceinline__ long long trace_now() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -439,7 +439,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
     const int sr0 = band * R;                      // first row of the band, in sweep order
     if (sr0 >= nrows) return;
     DGB_TRACE(long long tr_wait_up = 0; long long tr_n_wait = 0; long long tr_mbar = 0; long long tr_flow = 0; long long tr_steps = 0; long long tr_epi = 0;)
-    DGB_TRACE(if (lane == 0 && band < 8192) g_chain_trace[12 * band] = trace_now();)
+    DGB_TRACE(if (lane == 0 && band < 8192) g_chain_trace[16 * band] = trace_now();)
     const int Rv = min(R, nrows - sr0);            // rows of this band
     uint64_t *full = bars + w * NS;
     // lane -> (element row g of the band, scalar row r, column part): lanes beyond the band's rows shadow row 0
@@ -579,7 +579,7 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
         DGB_TRACE(long long tr0 = clock64();)
         if (!have && !mbar_wait(&full[s], (uint32_t)((n / NS) & 1), err)) return;
         have = false;
-        DGB_TRACE(if (n > 0) tr_mbar += clock64() - tr0; else if (lane == 0 && band < 8192) g_chain_trace[12 * band + 1] = trace_now();)
+        DGB_TRACE(if (n > 0) tr_mbar += clock64() - tr0; else if (lane == 0 && band < 8192) g_chain_trace[16 * band + 1] = trace_now();)
         DGB_TRACE(tr0 = clock64();)
         // ---- once per chunk: flow control and the global hand-overs ----
         if (pred == 1 && lane == 0) s_prog[w] = t0;                           // columns < t0 are consumed
@@ -736,10 +736,13 @@ k_gs_chain(const double *__restrict__ rec, double *__restrict__ rec_other, const
             }
         }
         DGB_TRACE(__syncwarp(); tr_epi += clock64() - tr0;)
+        // end of chunks 0, 1, 7, 63: how the distance to the band above develops along the row
+        DGB_TRACE(if (lane == 0 && band < 8192 && (n == 0 || n == 1 || n == 7 || n == 63))
+                      g_chain_trace[16 * band + 11 + (n == 0 ? 0 : n == 1 ? 1 : n == 7 ? 2 : 3)] = trace_now();)
     }
 #ifdef DGB_CHAIN_TRACE
     if (lane == 0 && band < 8192) {
-        long long *tr = g_chain_trace + 12 * band;
+        long long *tr = g_chain_trace + 16 * band;
         tr[8] = tr_steps;
         tr[9] = tr_epi;
         tr[10] = nchunks;
@@ -1726,6 +1729,6 @@ int dgb_build_gs_chain(const dgb_operator *op, void *stream) {
 #ifdef DGB_CHAIN_TRACE
 extern "C" int dgb_debug_chain_trace(long long *host_out, int n_bands) {
     if (n_bands > 8192) n_bands = 8192;
-    return (int)cudaMemcpyFromSymbol(host_out, dgb::g_chain_trace, sizeof(long long) * 12 * n_bands);
+    return (int)cudaMemcpyFromSymbol(host_out, dgb::g_chain_trace, sizeof(long long) * 16 * n_bands);
 }
 #endif

@@ -49,7 +49,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    out = np.zeros((min(nb, 8192), 12), dtype=np.int64)
+    out = np.zeros((min(nb, 8192), 16), dtype=np.int64)
     L.dgb_debug_chain_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     rc = L.dgb_debug_chain_trace(out.ctypes.data, out.shape[0])
     assert rc == 0, rc
@@ -81,6 +81,14 @@ def main():
     res["cycles_per_chunk"] = {"mbar_wait": float(np.median(cyc_mbar / nch)), "flow_control": float(np.median(cyc_flow / nch)),
                                "steps": float(np.median(out[:, 8] / nch)), "epilogue": float(np.median(out[:, 9] / nch)),
                                "wait_up": float(np.median(cyc_wait / nch)), "band0": [float(out[0, k] / nch[0]) for k in (5, 6, 8, 9, 4)]}
+    # distance (us) to the band above at the end of chunks 0, 1, 7, 63 and at the end of the row (ring hand-overs only)
+    ring = np.concatenate([[False], kind == "ring"])
+    for nm, col in (("chunk0", 11), ("chunk1", 12), ("chunk7", 13), ("chunk63", 14), ("end", 2)):
+        tcol = (out[:, col] - t0) * 1e-3
+        lag = tcol[1:] - tcol[:-1]
+        ok = ring[1:] & (out[1:, col] > 0) & (out[:-1, col] > 0)
+        if ok.any():
+            res[f"lag_ring_us@{nm}"] = {"median": float(np.median(lag[ok])), "mean": float(lag[ok].mean())}
     res["sum_lag_end_us"] = {k: float(lag_end[kind == k].sum()) for k in ("ring", "dsmem", "mailbox")}
     # when do bands start relative to their predecessor's end (a band that starts after its SM freed up)
     res["bands_started_after_t0_us"] = [float(v) for v in np.percentile(start, [0, 25, 50, 75, 100])]
