@@ -76,6 +76,7 @@ SMOOTHER_IDS = {"block_gauss_seidel_pyamg": 0, "block_jacobi": 1, "block_gauss_s
 FLAG_PERIODIC_I, FLAG_PERIODIC_J, FLAG_MINV, FLAG_GHOST_LO, FLAG_GHOST_HI = 1, 2, 4, 8, 16
 UNSUPPORTED = 100        # DGB_UNSUPPORTED
 COARSE_SMOOTHER, COARSE_DIRECT = 0, 1
+VCYCLE_ENTRY_PRIMED = 1  # DGB_VCYCLE_ENTRY_PRIMED
 
 # name -> (restype, argtypes); every symbol include/dgb200.h declares
 OP = ctypes.POINTER(Operator)
@@ -127,6 +128,7 @@ SIGNATURES = {
     "dgb_restrict_slab": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_prolong_add_slab": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dgb_vcycle": (c_i32, [ctypes.POINTER(Level), c_i32, ctypes.POINTER(VcycleOpts), c_vp, c_vp, c_vp, c_vp]),
+    "dgb_vcycle_ex": (c_i32, [ctypes.POINTER(Level), c_i32, ctypes.POINTER(VcycleOpts), c_vp, c_vp, c_vp, c_vp, c_i32]),
     "dgb_tables_create": (c_i32, [ctypes.POINTER(TablesDesc), ctypes.POINTER(c_vp)]),
     "dgb_tables_destroy": (None, [c_vp]),
     "dgb_metrics": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
@@ -154,7 +156,7 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.dgb_abi_version() != 5:
+    if L.dgb_abi_version() != 6:
         raise DgbError("libdgb200.so ABI version mismatch")
     if os.environ.get("DGB_KERNELS", "auto") == "generic":
         L.dgb_set_kernel_path(1)

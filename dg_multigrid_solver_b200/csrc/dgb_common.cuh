@@ -17,7 +17,10 @@ int sm_count();
 extern long long g_launches;   // kernels launched by this library (dgb_launch_count)
 int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direction, int32_t max_iterations,
              int32_t mode, int32_t check_residual, dgb_smoother_ctl *ctl, double *partials, double *sumsq,
-             double *r_keep, void *stream, void *event_after_last_pass = nullptr, bool u_is_zero = false);
+             double *r_keep, void *stream, void *event_after_last_pass = nullptr, bool u_is_zero = false,
+             bool entry_primed = false);
+// the smoother call on this operator opens with the fused entry residual (dgb_block_gs_entry_residual)
+bool gs_entry_fused(const dgb_operator *op);
 
 #define DGB_CUDA_OK(expr)                                                               \
     do {                                                                                \

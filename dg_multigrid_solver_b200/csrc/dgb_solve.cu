@@ -463,13 +463,17 @@ static int lexicographic_pass(const dgb_operator *op, const double *rhs, double 
 }
 
 namespace dgb {
+bool gs_entry_fused(const dgb_operator *op) {
+    return use_stream(op) && op->gs_chain != nullptr && op->gs_mailbox != nullptr && chain_supported(op->b, op->stencil) &&
+           chain_c_recurrence(op->stencil);
+}
 // Relaxation.block_gauss_seidel_pyamg on the device (dgfem/relaxation.py:198-218).  r_keep (optional): every
 // residual test also stores the residual vector, so that after the call r_keep == rhs - A u for the u the
 // smoother returns (the tests after an early exit are no-ops and u no longer changes) -- the V-cycle reuses it
 // for the restriction instead of evaluating the same residual again (dgfem/solver.py:150).
 int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direction, int32_t max_iterations,
              int32_t mode, int32_t check_residual, dgb_smoother_ctl *ctl, double *partials, double *sumsq,
-             double *r_keep, void *stream, void *event_after_last_pass, bool u_is_zero) {
+             double *r_keep, void *stream, void *event_after_last_pass, bool u_is_zero, bool entry_primed) {
     int rc = check_op(op);
     if (rc) return rc;
     DGB_ARG(ctl && partials && sumsq);
@@ -488,7 +492,11 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
         const bool chained = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
                              op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
                              chain_supported(op->b, op->stencil) && chain_c_recurrence(op->stencil);
-        if (chained) {
+        if (chained && entry_primed) {
+            // dgb_vcycle_ex: the caller ran dgb_block_gs_entry_residual on (rhs, u) itself -- *sumsq, r_keep and the
+            // first pass's right-hand sides are in place
+            last_dir = -first_dir;
+        } else if (chained) {
             // the entry residual shares its block reads with the dependency-free part of the first pass
             int grid = 1;
             rc = gs_chain_helper_residual(op, rhs, u, first_dir, r_keep, partials, &grid, (cudaStream_t)stream,

@@ -14,7 +14,8 @@ namespace dgb {
 // (dgfem/solver.py:143-147,196)
 static int smooth(const dgb_level &L, int smoother, int direction, double omega, const dgb_vcycle_opts &o,
                   int iterations, dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream,
-                  bool *have_residual = nullptr, void *u_final_event = nullptr, bool u_is_zero = false) {
+                  bool *have_residual = nullptr, void *u_final_event = nullptr, bool u_is_zero = false,
+                  bool entry_primed = false) {
     if (have_residual) *have_residual = false;
     if (iterations <= 0 || smoother != DGB_SMOOTHER_BLOCK_GS_PYAMG) {
         // no in-smoother hook: the event is recorded by the caller after the smoother returns
@@ -28,7 +29,7 @@ static int smooth(const dgb_level &L, int smoother, int direction, double omega,
         if (have_residual && o.check_residual) {
             *have_residual = true;
             return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, 1, ctl, partials, sumsq, L.r, stream,
-                            nullptr, u_is_zero);
+                            nullptr, u_is_zero, entry_primed);
         }
         return gs_pyamg(&L.op, L.rhs, L.u, direction, iterations, o.gs_mode, o.check_residual, ctl, partials, sumsq,
                         nullptr, stream, u_final_event, u_is_zero);
@@ -56,8 +57,11 @@ static int smooth(const dgb_level &L, int smoother, int direction, double omega,
 
 // u_zero: this level's iterate was just zeroed (solver.py:171) -- its first smoother call need not read the operator
 // for its entry residual (r = rhs) and first right-hand sides (c = Dinv rhs): same bits, a sixth of the bytes
+// entry_primed (finest level only): the caller has evaluated the pre-smoother's entry residual itself
+// (dgb_block_gs_entry_residual on this level's rhs, u, r and `sumsq`) -- dgb_vcycle_ex
 static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoother_ctl *ctl,
-                  double *partials, double *sumsq, void *stream, bool top = false, bool u_zero = false) {
+                  double *partials, double *sumsq, void *stream, bool top = false, bool u_zero = false,
+                  bool entry_primed = false) {
     const dgb_level &L = lv[k];
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
@@ -77,7 +81,7 @@ static int vcycle(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoo
     const dgb_level &C = lv[k - 1];
     bool have_r = false;
     if ((rc = smooth(L, L.smoother, L.direction, L.omega, o, L.pre_iterations, ctl + k, partials, sumsq, stream, &have_r,
-                     nullptr, u_zero)))
+                     nullptr, u_zero, entry_primed)))
         return rc;
     // residual = RHS - BSR @ u (solver.py:150); the pre-smoother's last residual test already evaluated exactly
     // this vector (same kernel, same inputs), so it is not computed twice
@@ -99,10 +103,8 @@ int vcycle_entry(const dgb_level *lv, int k, const dgb_vcycle_opts &o, dgb_smoot
     return vcycle(lv, k, o, ctl, partials, sumsq, stream, false, u_zero);
 }
 
-}  // namespace dgb
-
-extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
-                          dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream) {
+static int vcycle_args_ok(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
+                          dgb_smoother_ctl *ctl, double *partials, double *sumsq) {
     DGB_ARG(h_levels && h_opts && ctl && partials && sumsq && nlevels >= 1);
     DGB_ARG(h_opts->coarse_solver == DGB_COARSE_SMOOTHER ||
             (h_opts->coarse_solver == DGB_COARSE_DIRECT && h_opts->coarse_inverse != nullptr));
@@ -119,5 +121,30 @@ extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_
             }
         }
     }
+    return 0;
+}
+
+}  // namespace dgb
+
+extern "C" int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
+                          dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream) {
+    int rc = dgb::vcycle_args_ok(h_levels, nlevels, h_opts, ctl, partials, sumsq);
+    if (rc) return rc;
     return dgb::vcycle(h_levels, nlevels - 1, *h_opts, ctl, partials, sumsq, stream, true);
+}
+
+extern "C" int dgb_vcycle_ex(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
+                             dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream, int32_t flags) {
+    int rc = dgb::vcycle_args_ok(h_levels, nlevels, h_opts, ctl, partials, sumsq);
+    if (rc) return rc;
+    DGB_ARG((flags & ~DGB_VCYCLE_ENTRY_PRIMED) == 0);
+    const bool primed = (flags & DGB_VCYCLE_ENTRY_PRIMED) != 0;
+    if (primed) {
+        // only where the pre-smoother would itself open with dgb_block_gs_entry_residual
+        const dgb_level &L = h_levels[nlevels - 1];
+        if (!(nlevels >= 2 && L.smoother == DGB_SMOOTHER_BLOCK_GS_PYAMG && L.pre_iterations > 0 && h_opts->check_residual &&
+              h_opts->gs_mode == DGB_GS_LEXICOGRAPHIC && dgb::gs_entry_fused(&L.op)))
+            return DGB_UNSUPPORTED;
+    }
+    return dgb::vcycle(h_levels, nlevels - 1, *h_opts, ctl, partials, sumsq, stream, true, false, primed);
 }

@@ -37,6 +37,7 @@ class Solver:
         self._hier = None
         self.timings = {}
         self.graph_launches = self.graph_replays = 0
+        self.primed_cycles = 0           # V-cycles of solve_multigrid that started from the loop's own residual
 
     # ------------------------------------------------------------------------------------
     def solve(self):
@@ -175,43 +176,52 @@ class Solver:
             self._build_hierarchy()
         return self._hier
 
-    def _launch_vcycle(self, H, k):
-        rc = _lib.load().dgb_vcycle(H["levels"], k, ctypes.byref(H["opts"]), H["ctl"].data_ptr(),
-                                    H["partials"].data_ptr(), H["sumsq"].data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "dgb_vcycle")
+    def _launch_vcycle(self, H, k, primed=False):
+        rc = _lib.load().dgb_vcycle_ex(H["levels"], k, ctypes.byref(H["opts"]), H["ctl"].data_ptr(),
+                                       H["partials"].data_ptr(), H["sumsq"].data_ptr(), _lib.stream_ptr(),
+                                       _lib.VCYCLE_ENTRY_PRIMED if primed else 0)
+        if primed and rc == _lib.UNSUPPORTED:       # nothing was launched
+            return False
+        _lib.check(rc, "dgb_vcycle_ex")
+        return True
 
-    def _vcycle_device(self, k):
+    def _vcycle_device(self, k, primed=False):
         """One V-cycle (dgb_vcycle).  The launch sequence of a full cycle is fixed (the smoother's early exit is a
         device-side flag), so from the third call on it is replayed as one CUDA graph: the ~150 kernels of the
         coarse levels are shorter than their launch latency otherwise (`solver.b200.cuda graph: False` or
-        DGB_VCYCLE_GRAPH=0 keeps plain launches)."""
+        DGB_VCYCLE_GRAPH=0 keeps plain launches).  primed: the caller has just run dgb_block_gs_entry_residual on the
+        finest level (solve_multigrid's residual after the previous cycle), the cycle starts with its first pass;
+        returns False (nothing launched) when the library does not support that for this hierarchy."""
         H = self.hierarchy()
         use_graph = k == H["n"] and not H["opts"].u_final_event and H.get("graph_ok", True) and \
             os.environ.get("DGB_VCYCLE_GRAPH", "1") != "0" and self.settings.get("solver.b200.cuda_graph", True)
         if not use_graph:
-            return self._launch_vcycle(H, k)
-        if H.get("graph") is not None:
-            H["graph"].replay()
+            return self._launch_vcycle(H, k, primed)
+        gkey, ckey = ("graph_primed", "vcalls_primed") if primed else ("graph", "vcalls")
+        if H.get(gkey) is not None:
+            H[gkey].replay()
             self.graph_replays += 1
-            return
-        H["vcalls"] = H.get("vcalls", 0) + 1
-        if H["vcalls"] < 3:
-            return self._launch_vcycle(H, k)
+            return True
+        H[ckey] = H.get(ckey, 0) + 1
+        if H[ckey] < 3:
+            return self._launch_vcycle(H, k, primed)
         torch = _lib.require_cuda()
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = _lib.load().dgb_launch_count(0)
             with torch.cuda.graph(g):
-                self._launch_vcycle(H, k)
-            self.graph_launches = int(_lib.load().dgb_launch_count(0) - before)      # kernels one replay launches
-            H["graph"] = g
+                self._launch_vcycle(H, k, primed)
+            if not primed:
+                self.graph_launches = int(_lib.load().dgb_launch_count(0) - before)  # kernels one replay launches
+            H[gkey] = g
         except Exception:                    # capture is an optimisation: fall back to plain launches
             H["graph_ok"] = False
             torch.cuda.synchronize()
-            return self._launch_vcycle(H, k)
-        H["graph"].replay()
+            return self._launch_vcycle(H, k, primed)
+        H[gkey].replay()
         self.graph_replays += 1
+        return True
 
     def _check_divergence(self):
         """Host-side view of the device state, wherever the host synchronises anyway: the sticky `diverged`
@@ -295,20 +305,48 @@ class Solver:
         n_dof = float(nrow * b)
         st = _lib.stream_ptr()
 
+        # The residual the loop evaluates after a cycle (solver.py:119) is the entry residual the next cycle's
+        # pre-smoother opens with (relaxation.py:202: same operator, rhs and u).  Where that smoother call starts with
+        # the fused kernel (chained lexicographic sweep) the loop runs it itself and hands the cycle its outcome
+        # (dgb_vcycle_ex, DGB_VCYCLE_ENTRY_PRIMED): one evaluation of A u on the finest level per cycle instead of two.
+        L = _lib.load()
+        top = H["levels"][levels - 1]
+        first_dir = 1 if top.direction >= 0 else -1
+        state = {"primed": levels == H["n"] and levels >= 2 and bool(torch.equal(rhs_k, fine_rhs)) and
+                 os.environ.get("DGB_SOLVE_PRIME", "1") != "0"}
+
         def rms():
-            _lib.call("dgb_bsr_residual", fine_op, fine_rhs, u_k, None, H["partials"], H["sumsq"], None, st)
+            if state["primed"]:
+                rc = L.dgb_block_gs_entry_residual(ctypes.byref(fine_op), rhs_k.data_ptr(), u_k.data_ptr(), first_dir,
+                                                   r_k.data_ptr(), H["partials"].data_ptr(), H["sumsq"].data_ptr(), st)
+                if rc == _lib.UNSUPPORTED:
+                    state["primed"] = False
+                else:
+                    _lib.check(rc, "dgb_block_gs_entry_residual")
+            if not state["primed"]:
+                _lib.call("dgb_bsr_residual", fine_op, fine_rhs, u_k, None, H["partials"], H["sumsq"], None, st)
             return float(np.sqrt(H["sumsq"].item() / n_dof))
+
+        def cycle():
+            if state["primed"]:
+                if self._vcycle_device(levels, primed=True):
+                    self.primed_cycles += 1
+                    return
+                state["primed"] = False            # this hierarchy's pre-smoother opens differently: the plain cycle
+            self._vcycle_device(levels)
         n = 0
         residual_0 = rms()
+        norm = residual_0                          # solver.py:117,119 evaluate the same vector twice before cycle 1
         with np.errstate(divide="ignore", invalid="ignore"):
             while n < max_cycles:
-                residual = np.float64(rms()) / np.float64(residual_0)
+                residual = np.float64(norm) / np.float64(residual_0)
                 self.residuals.append(float(residual))
                 if residual < tol or np.isnan(residual) or np.isinf(residual):
                     break
-                self._vcycle_device(levels)
+                cycle()
                 n += 1
                 self._check_divergence()          # the reference leaves at the first diverging smoother call
+                norm = rms()
         self._pickle_residuals(fine)
         return u_k.cpu().numpy() if host else u_k.clone()
 

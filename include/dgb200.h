@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DGB_ABI_VERSION 5
+#define DGB_ABI_VERSION 6
 
 /* ---- status ------------------------------------------------------------------------- */
 int dgb_abi_version(void);
@@ -342,6 +342,18 @@ int dgb_dense_solve(const double *inverse, int32_t n, const double *rhs, double 
  * ctl: array of nlevels control blocks (device); partials/sumsq: workspaces. */
 int dgb_vcycle(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
                dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream);
+
+/* The same cycle for a caller that has just evaluated the finest level's residual itself -- Solver.solve_multigrid
+ * does, after every cycle (dgfem/solver.py:117-119), and that vector is exactly the entry residual the next cycle's
+ * pre-smoother opens with (dgfem/relaxation.py:202).  flags = DGB_VCYCLE_ENTRY_PRIMED: the caller ran
+ * dgb_block_gs_entry_residual(&levels[n-1].op, levels[n-1].rhs, levels[n-1].u, first direction of the pre-smoother,
+ * levels[n-1].r, partials, sumsq, stream) on the current u; the cycle then starts with the first pass (one residual
+ * evaluation of the finest level saved per cycle of a solve).  Returns DGB_UNSUPPORTED (nothing launched) when the
+ * finest level's pre-smoother does not open that way (other smoother / 2-colour mode / no residual tests / no
+ * chained kernel); flags = 0 is dgb_vcycle. */
+#define DGB_VCYCLE_ENTRY_PRIMED 1
+int dgb_vcycle_ex(const dgb_level *h_levels, int32_t nlevels, const dgb_vcycle_opts *h_opts,
+                  dgb_smoother_ctl *ctl, double *partials, double *sumsq, void *stream, int32_t flags);
 
 /* ---- K0-K3: DG assembly (Poisson) ------------------------------------------------------- */
 /* Basis / quadrature / geometry-operator tables of one level, uploaded once

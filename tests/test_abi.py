@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(lib)
     for name in _declared_symbols():
         assert hasattr(L, name), f"{name} declared in include/dgb200.h but not exported"
-    assert L.dgb_abi_version() == 5
+    assert L.dgb_abi_version() == 6
     assert L.dgb_partials_len() >= 1024
 
 

@@ -591,6 +591,29 @@ def test_midsize_vcycle_against_oracle():
     assert rel_err(u1, uo) < 1e-10
 
 
+@pytest.mark.parametrize("name,gs_mode", [("rect8_h24", "lexicographic"), ("c2", "lexicographic"), ("rect8_h24", "redblack")])
+def test_solve_loop_hands_its_residual_to_the_next_cycle(name, gs_mode, monkeypatch):
+    """solve_multigrid's residual after a cycle (dgfem/solver.py:119) is the next pre-smoother's entry residual
+    (relaxation.py:202): with the chained kernel the loop evaluates it once (dgb_block_gs_entry_residual +
+    dgb_vcycle_ex(DGB_VCYCLE_ENTRY_PRIMED)).  Same history and iterate as the plain loop; the 2-colour mode, whose
+    smoother opens differently, falls back to the plain cycle."""
+    out = {}
+    for prime in ("0", "1"):
+        monkeypatch.setenv("DGB_SOLVE_PRIME", prime)
+        d = build(CASES[name], gs_mode=gs_mode)
+        fine = d.grids[-1]
+        u = d.solver.solve_multigrid(len(d.grids), fine.RHS, np.zeros_like(fine.RHS))
+        out[prime] = (np.array(d.solver.residuals), u, d.solver.primed_cycles)
+    h0, u0, n0 = out["0"]
+    h1, u1, n1 = out["1"]
+    assert n0 == 0 and n1 == (len(h1) - 1 if gs_mode == "lexicographic" else 0)
+    assert len(h0) == len(h1)
+    assert np.allclose(h1, h0, rtol=1e-12, atol=1e-14)
+    assert rel_err(u1, u0) < 1e-12
+    if gs_mode == "lexicographic":
+        assert np.allclose(h1, golden(name)["residuals"], rtol=HIST_RTOL, atol=HIST_ATOL)
+
+
 def test_stokes_global_order_and_distributive_gauss_seidel():
     """global-order Stokes blocks (dgfem/discrete_system.py:416-745) and
     Relaxation.distributive_gauss_seidel with the `lsq` splitting (dgfem/relaxation.py:221-283) -- the
