@@ -268,6 +268,32 @@ def run_b200(args):
     ss0, _ = residual_norm(fine, fine.d_rhs, torch.zeros_like(u_k))
     res0 = float(np.sqrt(ss0.item() / n_dof))
 
+    # ---- a full solve (Solver.solve_multigrid: residual test + V-cycle per iteration, from u = 0 to 1e-6) ----------
+    solve = None
+    if args.solve:
+        import tempfile
+        u0 = torch.zeros_like(u_k)
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:       # the loop pickles its residual history below the cwd (solver.py:128-138)
+            os.chdir(tmp)
+            try:
+                for rep in range(2):         # the first run captures the graph of the cycle that follows the loop's residual
+                    solver.residuals = []
+                    solver.primed_cycles = 0
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    solver.solve_multigrid(nlev, fine.d_rhs, u0)
+                    torch.cuda.synchronize()
+                    dt_solve = time.perf_counter() - t0
+            finally:
+                os.chdir(cwd)
+        ncyc = len(solver.residuals) - 1
+        solve = {"cycles": ncyc, "s": dt_solve, "ms_per_iteration": 1e3 * dt_solve / max(ncyc, 1),
+                 "final_normalised_residual": solver.residuals[-1], "tolerance": 1e-6,
+                 "cycles_started_from_the_loops_residual": solver.primed_cycles,
+                 "timing": "host wall clock around Solver.solve_multigrid (device-resident rhs/u, one host sync per cycle)"}
+        rhs_k.copy_(fine.d_rhs)
+
     # ---- end to end through the reference-facing call, host buffers --------------------------
     h_rhs = torch.empty(n_dof, dtype=torch.float64, pin_memory=True)
     h_u = torch.zeros(n_dof, dtype=torch.float64, pin_memory=True)
@@ -420,6 +446,12 @@ def run_b200(args):
               "frac_bytes_min_of_nominal_8TBs": bytes_min / vc_t / 1e9 / 8000.0,
               "normalised_residual_after_timed_cycles": res_after / res0,
               "cycles_run": args.warmup + args.steps}
+    if solve is not None:
+        # per iteration of the loop: the cycle's bytes_min plus the loop's own residual of the finest level
+        it_bytes = bytes_min + ab["residual"]
+        solve["bytes_min_per_iteration"] = it_bytes
+        solve["frac_bytes_min"] = it_bytes * solve["cycles"] / solve["s"] / 1e9 / peak
+        solve["dof_per_s"] = n_dof / solve["s"]
     # device memory the hierarchy holds (operator, inverse diagonal blocks, smoother streams, vectors)
     mem = {"data": 0, "dinv": 0, "gs_chain": 0, "gs_data": 0, "mailbox": 0, "vectors": 0}
     for g in d.grids:
@@ -451,7 +483,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "solve": solve,
             "kernels": kern, "vcycle": vcycle, "memory": mem,
             "apply_dof_per_s": n_dof / (k_apply[0] * 1e-3),
             "vcycle_dof_per_s": n_dof * value,
@@ -650,6 +682,7 @@ def main():
     ap.add_argument("--check-residual", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solve", type=int, default=1, help="also time a full Solver.solve_multigrid run (u = 0 -> 1e-6)")
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
                     help="c3 = the V-cycle workload (BASELINE configs[2], default); c4 / c5 = configs[3] / configs[4]")
     ap.add_argument("--p5-apply", type=int, default=1,
