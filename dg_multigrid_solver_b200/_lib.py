@@ -202,6 +202,8 @@ def call(name, *args):
             conv.append(a)
     rc = getattr(L, name)(*conv)
     check(rc, name)
+    if os.environ.get("DGB_SYNC_CALLS") == "1":      # diagnostics (tools/profile_setup.py): device time lands on its call
+        require_cuda().cuda.synchronize()
     return rc
 
 

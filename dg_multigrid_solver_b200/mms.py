@@ -23,6 +23,7 @@ def _torch_namespace():
 
 class Field:
     """One scalar expression in (x, y), callable on numpy arrays or torch tensors."""
+    CHUNK = 1 << 22           # entries per slice of a device evaluation
 
     def __init__(self, expr):
         self.expr = sym.sympify(expr)
@@ -43,7 +44,17 @@ class Field:
             return torch.full_like(X, self._const)
         if self._th is None:
             self._th = sym.lambdify(self._xy, self.expr, modules=[_torch_namespace()])
-        return self._th(X, Y)
+        # the generated expression makes a fresh temporary per operation: on a whole level (2048^2 elements x 16
+        # points = 537 MB each) every one of them is a cudaMalloc.  Slices along the element axis keep the temporaries
+        # in blocks the caching allocator hands back at once; same values, entry by entry
+        per = max(1, X[0].numel()) if X.dim() > 0 else 1
+        if X.dim() == 0 or X.numel() <= self.CHUNK:
+            return self._th(X, Y)
+        out = torch.empty(X.shape, dtype=torch.float64, device=X.device)
+        step = max(1, self.CHUNK // per)
+        for i0 in range(0, X.shape[0], step):
+            out[i0:i0 + step] = self._th(X[i0:i0 + step], Y[i0:i0 + step])
+        return out
 
 
 class PoissonMMS:

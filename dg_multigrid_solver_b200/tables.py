@@ -125,15 +125,20 @@ class Tables:
         sub_vol = np.zeros((self.nq, 2), dtype=np.int32)
         sub_face = np.zeros((4, nq1, 2), dtype=np.int32)
 
+        k2 = 1 + 2 * np.arange(cf)
+
         def locate(R, S):
-            # first containing fine sub-element, n outer / m inner (element.py:278-287)
-            for n in range(cf):
-                for m in range(cf):
-                    r = (2 * R + 2 - delta * (1 + m * 2)) / delta
-                    s = (2 * S + 2 - delta * (1 + n * 2)) / delta
-                    if -1 <= r <= 1 and -1 <= s <= 1:
-                        return m, n, r, s
-            raise RuntimeError("coarse quadrature point not located in any fine element")
+            # first containing fine sub-element, n outer / m inner (element.py:278-287).  r depends on m only and s on
+            # n only, so the first match of the double loop is (first n whose s fits, first m whose r fits); the two
+            # expressions are the reference's, evaluated for all m (n) at once with the same operations
+            r_all = (2 * R + 2 - delta * k2) / delta
+            s_all = (2 * S + 2 - delta * k2) / delta
+            ok_r = (-1 <= r_all) & (r_all <= 1)
+            ok_s = (-1 <= s_all) & (s_all <= 1)
+            if not (ok_r.any() and ok_s.any()):
+                raise RuntimeError("coarse quadrature point not located in any fine element")
+            m, n = int(np.argmax(ok_r)), int(np.argmax(ok_s))
+            return m, n, float(r_all[m]), float(s_all[n])
 
         def put_face(f, idx, m, n, r, s):
             L, Dr, Ds = self._ops_at([r], [s])
