@@ -44,12 +44,36 @@ def test_tables_match_oracle_tables():
     assert np.array_equal(h_restriction()[0], g["R0"]) and np.array_equal(p_restriction(3, 5), g["R2"])
 
 
+def test_mms_fields_in_slices_equal_whole_evaluation():
+    """Device evaluation of the manufactured solution runs in slices along the element axis (mms.Field.CHUNK): same
+    values entry by entry as one evaluation, and as the NumPy evaluation (dgfem/dgfem.py:410-483) to rounding."""
+    import torch
+    from dg_multigrid_solver_b200 import mms
+    f = mms.Field("-2*sin(pi*x)**2*sin(pi*y)*cos(pi*y)")
+    g = torch.Generator().manual_seed(3)
+    vol = torch.rand(301, 7, 9, dtype=torch.float64, generator=g) * 2 - 1
+    X, Y = vol[:, 5, :], vol[:, 6, :]                      # strided views, as assemble_RHS_Poisson passes them
+    whole = f(X, Y)
+    old = mms.Field.CHUNK
+    try:
+        mms.Field.CHUNK = 64
+        sliced = f(X, Y)
+        face = torch.rand(50, 4, 8, 3, dtype=torch.float64, generator=g)
+        sliced4 = f(face[:, :, 3, :], face[:, :, 4, :])
+    finally:
+        mms.Field.CHUNK = old
+    assert sliced.shape == whole.shape and sliced.is_contiguous() and torch.equal(sliced, whole)
+    assert np.abs(whole.numpy() - f(X.numpy(), Y.numpy())).max() < 1e-14
+    assert torch.equal(sliced4, f(face[:, :, 3, :], face[:, :, 4, :]))
+    assert torch.equal(mms.Field("3.5")(X, Y), torch.full_like(X, 3.5))
+
+
 def test_coarse_tables_follow_reference_point_location():
     """cf = 2, 4, 8: sub-element offsets and local coordinates (element.py:273-310, App. B.12)."""
     from dg_multigrid_solver_b200.tables import Tables
     from dgoracle import geometry as og
     from dgoracle import tables as ot
-    for cf in (2, 4, 8):
+    for cf in (2, 4, 8, 16, 64, 512):           # 512: the coarsest level of the 2048^2 bench hierarchy
         T, O = Tables(2, 1, cf=cf), ot.LevelTables(2, 1)
         for (iR, iS, m, n, r, s) in og.coarse_point_map(O, cf):
             q = iR + T.nq1 * iS
@@ -57,8 +81,9 @@ def test_coarse_tables_follow_reference_point_location():
             L, Dr, Ds = O.point_ops(r, s)
             assert np.allclose(T.GX[q], L[0], atol=1e-14)
             assert np.allclose(T.GR[q], cf * (Dr @ O.L_gg)[0], atol=1e-12)
-        # B.12: for cf >= 8 the "imin" face is sampled from an interior fine element
-        assert T.sub_face[0, 0, 0] == (0 if cf <= 4 else 1)
+        # B.12: for cf >= 8 the "imin" face is sampled from an interior fine element -- the one that holds the
+        # first volume point
+        assert T.sub_face[0, 0, 0] == int((T.r_int[0] + 1.0) / (2.0 / cf)) and (T.sub_face[0, 0, 0] > 0) == (cf >= 8)
 
 
 def test_plot3d_reader_matches_oracle_reader():
