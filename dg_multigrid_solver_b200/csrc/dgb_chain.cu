@@ -1069,8 +1069,9 @@ k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices
             }
             const int j = e / Ni, i = e - j * Ni;
             double *mine = rec + (size_t)chain_loc<B>(S_, dir, i, j) * REC + ChainCfg<B>::c_off(r);
-            *reinterpret_cast<double2 *>(mine) = make_double2(tt, td);   // c_e and d_e = Dinv_e rhs_e (for both sweep directions)
-            rec_other[(size_t)chain_loc<B>(S_, -dir, i, j) * REC + ChainCfg<B>::d_off(r)] = td;
+            // c_e and d_e = Dinv_e rhs_e.  The opposite direction's record gets its (c, d) pair from the chain pass that
+            // follows (its stores carry d along): an 8-byte store of d here would only half-fill sectors of that stream
+            *reinterpret_cast<double2 *>(mine) = make_double2(tt, td);
         }
         __syncthreads();
     }
