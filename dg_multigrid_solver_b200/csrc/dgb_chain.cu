@@ -1009,9 +1009,9 @@ template <int B, bool RES>
 __global__ void __launch_bounds__(HelperCfg<B>::NT, RES ? ((B > 4 && B <= 16) ? 5 : 6) : 8)
 k_gs_helper(const double *__restrict__ data, const int32_t *__restrict__ indices, const int32_t *__restrict__ indptr,
             const double *__restrict__ dinv, const double *__restrict__ rhs, const double *__restrict__ x,
-            double *rec, double *rec_other, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
+            double *rec, Stencil S_, int dir, const int32_t *__restrict__ skip, double *r_out,
             double *partials, int x_zero /* x == 0 (coarse-level initial guess, solver.py:171): no block is read */) {
-    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
+    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC;
     if (skip != nullptr && *skip != 0) return;
     __shared__ double s_rsum[EPB * B];
     __shared__ double s_rhs[EPB * B];
@@ -1215,7 +1215,7 @@ __global__ void __launch_bounds__(HelperCfg<B>::NT)
 k_gs_edge_helper(const double *__restrict__ data, const int32_t *__restrict__ indices,
                  const int32_t *__restrict__ indptr, const double *__restrict__ dinv, const double *__restrict__ x,
                  double *rec, Stencil S_, int dir, const int32_t *__restrict__ skip) {
-    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC, B2 = B * B;
+    constexpr int EPB = HelperCfg<B>::EPB, REC = ChainCfg<B>::REC;
     if (skip != nullptr && *skip != 0) return;
     __shared__ double s_t[EPB * B];
     const int el = threadIdx.x / B, r = threadIdx.x - el * B;
@@ -1504,7 +1504,7 @@ static int chain_pass_t(const dgb_operator *op, const double *rhs, double *x, in
         DGB_LAUNCH_OK();
     }
     if (!have_c && g_gs_variant != 22) {        // (21 / 22: time the two launches separately, results are then meaningless)
-        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
+        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec,
                                                       S_, dir, skip, nullptr, nullptr, 0);
         DGB_LAUNCH_OK();
     }
@@ -1523,13 +1523,12 @@ static int helper_residual_t(const dgb_operator *op, const double *rhs, const do
     using H = HelperCfg<B>;
     const Stencil S_ = make_stencil(op->Ni, op->Nj, op->stencil);
     double *rec = op->gs_chain + (dir > 0 ? 0 : chain_dir_len(B, S_));
-    double *rec_other = op->gs_chain + (dir > 0 ? chain_dir_len(B, S_) : 0);
     const int count = (S_.ja1 - S_.ja0) * S_.Ni;
     int grid = (count + H::EPB - 1) / H::EPB;
     constexpr int occ = (B > 4 && B <= 16) ? 5 : 6;
     if (grid > sm_count() * occ) grid = sm_count() * occ;    // one wave at the occupancy __launch_bounds__ asks for
     if (grid > kMaxPartials) grid = kMaxPartials;
-    k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other, S_,
+    k_gs_helper<B, true><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, S_,
                                                  dir, nullptr, r, partials, x_zero ? 1 : 0);
     DGB_LAUNCH_OK();
     *grid_out = grid;
@@ -1661,7 +1660,7 @@ static int chain_pass_big(const dgb_operator *op, const double *rhs, double *x, 
         DGB_LAUNCH_OK();
     }
     if (!have_c && g_gs_variant != 22) {
-        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec, rec_other,
+        k_gs_helper<B, false><<<grid, H::NT, 0, st>>>(op->data, op->indices, op->indptr, op->dinv, rhs, x, rec,
                                                       S_, dir, skip, nullptr, nullptr, 0);
         DGB_LAUNCH_OK();
     }

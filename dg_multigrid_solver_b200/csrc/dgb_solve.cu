@@ -620,7 +620,6 @@ int dgb_bsr_residual_colour(const dgb_operator *op, const double *rhs, const dou
     if (rc) return rc;
     DGB_ARG(x && rhs && partials && sumsq && (relaxed == 0 || relaxed == 1));
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = op->Ni * op->Nj;
     int grid = 1;
     Sel sel{3, 1 - relaxed, op->Ni, op->Nj, shift & 1, ((op->Ni + 1) / 2) * op->Nj, nullptr};
     DGB_DISPATCH_B_ANY(op->b, grid = rows_grid(sel.count, RowCfg<B>::EPB, rows_occupancy<B, MODE_RESIDUAL>());
@@ -762,7 +761,6 @@ int dgb_block_gs_pass(const dgb_operator *op, const double *rhs, double *x, int3
     DGB_ARG(op->dinv && rhs && x);
     DGB_ARG(direction == 1 || direction == -1);
     cudaStream_t st = (cudaStream_t)stream;
-    const int N = op->Ni * op->Nj;
     if (mode == DGB_GS_REDBLACK) {
         for (int k = 0; k < 2; ++k) {
             const int colour = direction > 0 ? k : 1 - k;
