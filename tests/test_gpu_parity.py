@@ -47,6 +47,32 @@ def test_assembled_levels_match_reference(mg):
         assert np.array_equal(R, g[f"R{k}"]) and np.array_equal(P, g[f"P{k}"])
 
 
+def test_element_metrics_match_reference(mg):
+    """a3 (dgfem/element.py:52-130,242-356): k_metrics' per-point arrays of the first and the last element of every
+    level -- J, rx, sx, ry, sy and the point coordinates at the volume points, the face Jacobians and unit normals of
+    the four faces -- against the values the reference's Element objects hold (h-coarsened levels included)."""
+    name, g, d = mg
+    if "L0_e00_J" not in g.files:
+        pytest.skip("light fixture")
+    for k, grid in enumerate(d.grids):
+        vol = grid.d_vol.cpu().numpy()                 # [N][7][nq]: J, rx, sx, ry, sy, x, y
+        face = grid.d_face.cpu().numpy()               # [N][4][8][nq1]: J_f, alpha, beta, x, y, nx, ny, -
+        scale = max(np.abs(g[f"L{k}_e00_{key}"]).max() for key in ("rx", "sx", "ry", "sy"))
+        for tag, m in (("e00", 0), ("eNN", grid.Ni * grid.Nj - 1)):
+            for c, key in enumerate(("J", "rx", "sx", "ry", "sy")):
+                ref = np.ravel(g[f"L{k}_{tag}_{key}"], order="F")      # point index r-fastest
+                sc = np.abs(ref).max() if key == "J" else scale
+                assert np.abs(vol[m, c] - ref).max() < 1e-12 * sc, (name, k, tag, key)
+            for f, fname in enumerate(("imin", "imax", "jmin", "jmax")):
+                ref = g[f"L{k}_{tag}_J_{fname}"]
+                assert np.abs(face[m, f, 0] - ref).max() < 1e-12 * np.abs(ref).max(), (name, k, tag, fname)
+        for f, fname in enumerate(("imin", "imax", "jmin", "jmax")):
+            n = g[f"L{k}_e00_n_{fname}"]
+            assert np.abs(face[0, f, 5] - n[:, 0]).max() < 1e-12 and np.abs(face[0, f, 6] - n[:, 1]).max() < 1e-12
+        assert rel_err(vol[0, 5], np.ravel(g[f"L{k}_e00_xint"], order="F")) < 1e-13
+        assert rel_err(vol[0, 6], np.ravel(g[f"L{k}_e00_yint"], order="F")) < 1e-13
+
+
 def test_apply_and_smoother_calls(mg):
     from dg_multigrid_solver_b200.relaxation import Relaxation, bsr_apply
     name, g, d = mg
