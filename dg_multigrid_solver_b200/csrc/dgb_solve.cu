@@ -225,16 +225,16 @@ static int rows_grid(int count, int epb, int occ = 8) {
 
 // ---------------------------------------------------------------------------------------
 // smoother control (device-side early exit; relaxation.py:202-216)
-__global__ void k_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, double n) {
-    ctl->res0 = sqrt(*sumsq / n);
+__device__ __forceinline__ void smoother_begin(dgb_smoother_ctl *ctl, double sumsq, double n) {
+    ctl->res0 = sqrt(sumsq / n);
     ctl->ratio = 1.0;
     ctl->skip = ctl->diverged;      // `diverged` is sticky (only the host clears it): nothing runs after a divergence
     ctl->iters = 0;
     ctl->calls += 1;
 }
-__global__ void k_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, double n) {
+__device__ __forceinline__ void smoother_check(dgb_smoother_ctl *ctl, double sumsq, double n) {
     if (ctl->skip) return;
-    const double ratio = sqrt(*sumsq / n) / ctl->res0;
+    const double ratio = sqrt(sumsq / n) / ctl->res0;
     ctl->ratio = ratio;
     ctl->iters += 1;
     if (ratio < 1e-6) {
@@ -242,6 +242,27 @@ __global__ void k_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, dou
     } else if (ratio > 1e10) {
         ctl->diverged = 1;
         ctl->skip = 1;
+    }
+}
+__global__ void k_smoother_begin(dgb_smoother_ctl *ctl, const double *sumsq, double n) { smoother_begin(ctl, *sumsq, n); }
+__global__ void k_smoother_check(dgb_smoother_ctl *ctl, const double *sumsq, double n) { smoother_check(ctl, *sumsq, n); }
+
+// k_sum_partials followed by the smoother's test on the sum (MODE 1: dgb_smoother_begin, 2: dgb_smoother_check) in one
+// launch: the chained smoother runs this pair after its entry residual and after every iteration, 61 times per V-cycle
+// of C3, and a kernel of a few microseconds costs its launch gap
+template <int MODE>
+__global__ void __launch_bounds__(1024)
+k_sum_partials_ctl(const double *__restrict__ partials, int n, double *out, const int32_t *__restrict__ skip,
+                   dgb_smoother_ctl *ctl, double ndof) {
+    if (skip != nullptr && *skip != 0) return;      // after an early exit both halves are no-ops
+    __shared__ double s_red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) v += partials[i];
+    const double t = block_sum<1024>(v, s_red);
+    if (threadIdx.x == 0) {
+        *out = t;
+        if (MODE == 1) smoother_begin(ctl, t, ndof);
+        else smoother_check(ctl, t, ndof);
     }
 }
 
@@ -487,6 +508,7 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
     const bool chained_loop = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
                               op->gs_chain != nullptr && op->gs_mailbox != nullptr &&
                               chain_supported(op->b, op->stencil) && chain_c_recurrence(op->stencil);
+    bool begun = false;    // the entry test already ran inside the reduction kernel
     if (check_residual) {
         const int first_dir = direction >= 0 ? +1 : -1;
         const bool chained = mode == DGB_GS_LEXICOGRAPHIC && max_iterations > 0 && use_stream(op) &&
@@ -502,9 +524,10 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
             rc = gs_chain_helper_residual(op, rhs, u, first_dir, r_keep, partials, &grid, (cudaStream_t)stream,
                                           u_is_zero && g_gs_variant != 42);
             if (rc) return rc;
-            k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, nullptr);
+            k_sum_partials_ctl<1><<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, nullptr, ctl, (double)n);
             DGB_LAUNCH_OK();
             last_dir = -first_dir;          // the first pass finds its c in place
+            begun = true;
         } else if (mode == DGB_GS_REDBLACK && max_iterations > 0 && op->stencil >= 0 && g_gs_variant != 43) {
             // the first colour of the first pass is relaxed by the kernel that evaluates its entry residual
             entry_colour = first_dir > 0 ? 0 : 1;
@@ -514,8 +537,7 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
             rc = dgb_bsr_residual(op, rhs, u, r_keep, partials, sumsq, nullptr, stream);
             if (rc) return rc;
         }
-        rc = dgb_smoother_begin(ctl, sumsq, n, stream);
-        if (rc) return rc;
+        if (!begun && (rc = dgb_smoother_begin(ctl, sumsq, n, stream))) return rc;
     }
     const int32_t *skip = check_residual ? &ctl->skip : nullptr;
     // 2-colour mode: relaxing a colour twice in a row with nothing in between recomputes the same values bit for bit
@@ -547,8 +569,9 @@ int gs_pyamg(const dgb_operator *op, const double *rhs, double *u, int32_t direc
                 int grid = 1;
                 rc = gs_chain_residual(op, u, last_dir, r_keep, partials, &grid, skip, (cudaStream_t)stream);
                 if (rc) return rc;
-                k_sum_partials<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, skip);
+                k_sum_partials_ctl<2><<<1, 1024, 0, (cudaStream_t)stream>>>(partials, grid, sumsq, skip, ctl, (double)n);
                 DGB_LAUNCH_OK();
+                continue;                   // the test ran inside the reduction kernel
             } else if (mode == DGB_GS_REDBLACK && last_colour >= 0 && op->stencil >= 0) {
                 rc = dgb_bsr_residual_colour(op, rhs, u, r_keep, last_colour, 0, partials, sumsq, skip, stream);
                 if (rc) return rc;
