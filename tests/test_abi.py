@@ -59,6 +59,25 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     assert got == want
 
 
+def test_ctypes_constants_match_the_header():
+    """Every #define the Python side mirrors (flags, sweep modes, transfer kinds, smoother ids, return codes)."""
+    from dg_multigrid_solver_b200 import _lib
+    src = open(os.path.join(REPO, "include", "dgb200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"^#define (DGB_[A-Z0-9_]+)\s+(-?\d+)", src, flags=re.M)}
+    want = {"DGB_FLAG_PERIODIC_I": _lib.FLAG_PERIODIC_I, "DGB_FLAG_PERIODIC_J": _lib.FLAG_PERIODIC_J,
+            "DGB_FLAG_MINV": _lib.FLAG_MINV, "DGB_FLAG_GHOST_LO": _lib.FLAG_GHOST_LO, "DGB_FLAG_GHOST_HI": _lib.FLAG_GHOST_HI,
+            "DGB_GS_LEXICOGRAPHIC": _lib.GS_LEXICOGRAPHIC, "DGB_GS_REDBLACK": _lib.GS_REDBLACK,
+            "DGB_GS_SLAB_LEXICOGRAPHIC": _lib.GS_SLAB_LEXICOGRAPHIC, "DGB_TRANSFER_P": _lib.TRANSFER_P,
+            "DGB_TRANSFER_H": _lib.TRANSFER_H, "DGB_UNSUPPORTED": _lib.UNSUPPORTED,
+            "DGB_COARSE_SMOOTHER": _lib.COARSE_SMOOTHER, "DGB_COARSE_DIRECT": _lib.COARSE_DIRECT,
+            "DGB_VCYCLE_ENTRY_PRIMED": _lib.VCYCLE_ENTRY_PRIMED,
+            "DGB_SMOOTHER_BLOCK_GS_PYAMG": _lib.SMOOTHER_IDS["block_gauss_seidel_pyamg"],
+            "DGB_SMOOTHER_BLOCK_JACOBI": _lib.SMOOTHER_IDS["block_jacobi"],
+            "DGB_SMOOTHER_BLOCK_GS": _lib.SMOOTHER_IDS["block_gauss_seidel"]}
+    for name, value in want.items():
+        assert defs[name] == value, name
+
+
 def test_product_has_no_cpu_path():
     """Without a GPU the product refuses to run (no oracle / CPU fallback on the product path)."""
     import torch
