@@ -483,6 +483,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "graph_replays": solver.graph_replays,
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "solve": solve,
             "kernels": kern, "vcycle": vcycle, "memory": mem,
             "apply_dof_per_s": n_dof / (k_apply[0] * 1e-3),
